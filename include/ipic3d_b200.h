@@ -1,0 +1,114 @@
+/*
+ * ipic3d_b200.h — C ABI of the B200-native particle hot path of AllScale iPIC3D.
+ *
+ * This is the drop-in boundary: plain C types, caller-allocated buffers, no callbacks, no torch
+ * types.  It is what the reference's C++ entry point
+ *     simulateSteps<Projector,FieldSolver,Mover>(numSteps, Universe&)
+ *                                   (reference code/app/include/ipic3d/app/simulator.h:42-47,127-242)
+ * calls underneath in this repository (see host/include/ipic3d/app/simulator.h and INTEGRATION.md).
+ *
+ * Data conventions (all doubles are IEEE binary64, all arrays are dense, caller-owned):
+ *   cells     : N = nx*ny*nz, flattened (x*ny + y)*nz + z           (reference cell.h:521-523)
+ *   particles : AoS of 8 doubles {x,y,z,vx,vy,vz,q,qom} = reference `struct Particle`
+ *               (particle.h:9-19), stored cell-major in canonical per-cell order.
+ *   field     : (nx+3)(ny+3)(nz+3) nodes x 9 doubles {E.xyz,B.xyz,Bext.xyz} = `FieldNode`   (field.h:14-18)
+ *   bcfield   : (nx+2)(ny+2)(nz+2) cells x 3 doubles {Bc.xyz}          = `BcFieldCell` (field.h:20-23)
+ *   density   : (nx+1)(ny+1)(nz+1) nodes x 3 doubles {J.xyz}           = `DensityNode` (field.h:25-27)
+ *   all three flattened like the cells (last index fastest), sizes as in universe.h:36.
+ *
+ * Every function returns 0 on success and a negative ipic_status on failure; the message of the
+ * last failure on the calling thread is available from ipic_last_error().  There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails with IPIC_ERR_CUDA.
+ */
+#ifndef IPIC3D_B200_H
+#define IPIC3D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+	IPIC_OK            =  0,
+	IPIC_ERR_ARG       = -1,   /* bad argument / state */
+	IPIC_ERR_CUDA      = -2,   /* CUDA runtime failure (incl. no device) */
+	IPIC_ERR_CAPACITY  = -3,   /* caller buffer too small */
+	IPIC_ERR_COMM      = -4,   /* NCCL failure / not initialised */
+	IPIC_ERR_INTERNAL  = -5
+} ipic_status;
+
+/* POD mirror of ipic3d::UniverseProperties (reference universe_properties.h:52-75). */
+typedef struct {
+	int64_t size[3];              /* grid size in cells                    (:57)  */
+	double  cellWidth[3];         /*                                       (:59)  */
+	double  dt;                   /*                                       (:61)  */
+	double  speedOfLight;         /*                                       (:63)  */
+	double  planetRadius;         /*                                       (:65)  */
+	double  objectCenter[3];      /*                                       (:67)  */
+	double  origin[3];            /*                                       (:70)  */
+	double  externalMagneticField[3]; /*                                   (:72)  */
+} ipic_props;
+
+/* Step flags: which of the reference's policy functors are active (simulator.h:246-275). */
+enum {
+	IPIC_MOVER_DIPOLE_ANALYTIC = 0u,      /* detail::default_particle_mover as shipped: E=0, analytic dipole B (cell.h:896-964) */
+	IPIC_MOVER_INTERPOLATED    = 1u << 0, /* the commented-out corner gather + trilinearInterpolationF2P (cell.h:905-937, :867-885) */
+	IPIC_PROJECT_CURRENT       = 1u << 1, /* detail::default_particle_to_field_projector → projectToDensityField (cell.h:787-824) */
+	IPIC_SOLVER_FORWARD        = 1u << 2, /* detail::forward_field_solver  → solveFieldForward  (field.h:294-337) */
+	IPIC_SOLVER_LEAPFROG       = 1u << 3, /* detail::leapfrog_field_solver → solveFieldLeapfrog (field.h:342-402) */
+	IPIC_UPDATE_BOUNDARIES     = 1u << 4, /* updateFieldsOnBoundaries before the solve (field.h:407-440, simulator.h:204) */
+	IPIC_SKIP_MIGRATION        = 1u << 5  /* diagnostics only: run mover without export/import */
+};
+
+typedef struct ipic_ctx ipic_ctx;
+
+/* Library / device ------------------------------------------------------------------------- */
+const char* ipic_last_error(void);
+const char* ipic_version(void);
+int  ipic_device_count(int* count);
+
+/* Context: one z-slab of the universe on one GPU.  For a single GPU the slab is the whole
+ * universe (rank 0 of 1).  Replaces the locals of simulateSteps (TransferBuffers, scratch;
+ * simulator.h:153-156). `device` is a CUDA ordinal. */
+int  ipic_create(const ipic_props* props, int device, ipic_ctx** out);
+int  ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, ipic_ctx** out);
+int  ipic_destroy(ipic_ctx* ctx);
+
+/* Multi-GPU wiring (z-slab neighbours, NCCL send/recv).  unique_id is NCCL's 128-byte id,
+ * produced on rank 0 by ipic_comm_unique_id and distributed by the caller. */
+int  ipic_comm_unique_id(void* unique_id_128);
+int  ipic_comm_init(ipic_ctx* ctx, const void* unique_id_128);
+
+/* State transfer.  Replaces direct access to universe.cells / .field / .bcfield / .currentDensity
+ * (universe.h:12-27).  `counts` has one entry per cell of the GLOBAL grid when the context is the
+ * whole universe, or of the slab (nx*ny*nz_local, same flatten) for slab contexts. */
+int  ipic_upload_cells(ipic_ctx* ctx, const uint64_t* counts, const double* particles_aos);
+int  ipic_download_cells(ipic_ctx* ctx, uint64_t* counts, double* particles_aos, uint64_t capacity_particles);
+int  ipic_cell_counts(ipic_ctx* ctx, uint64_t* counts);
+int  ipic_total_particles(ipic_ctx* ctx, uint64_t* total);
+int  ipic_upload_fields(ipic_ctx* ctx, const double* field, const double* bcfield, const double* density);
+int  ipic_download_fields(ipic_ctx* ctx, double* field, double* bcfield, double* density);
+
+/* The hot path: numSteps iterations of the loop body of simulateSteps (simulator.h:181-230).
+ * Blocking; returns after the device is idle.  t_first / t_rest (seconds, may be NULL) mirror
+ * DurationMeasurement{firstStep, remainingSteps} (simulator.h:37-40). */
+int  ipic_step(ipic_ctx* ctx, uint64_t num_steps, uint32_t flags, double* t_first, double* t_rest);
+
+/* Same, but only enqueues the work on the context's stream(s); pair with ipic_sync. */
+int  ipic_step_async(ipic_ctx* ctx, uint64_t num_steps, uint32_t flags);
+int  ipic_sync(ipic_ctx* ctx);
+
+/* Invariant check mirroring verifyCorrectParticlesPositionInCell (cell.h:1168-1184): number of
+ * particles outside the closed box of their cell. */
+int  ipic_count_misplaced(ipic_ctx* ctx, uint64_t* misplaced);
+
+/* Measurement support: device time (ms) of the mover / import kernels accumulated since the last
+ * reset, and the number of kernel launches issued. */
+int  ipic_profile_reset(ipic_ctx* ctx);
+int  ipic_profile_get(ipic_ctx* ctx, double* mover_ms, double* import_ms, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPIC3D_B200_H */
