@@ -1,0 +1,217 @@
+"""ctypes binding of include/ipic3d_b200.h (the drop-in C ABI).  No torch types cross this boundary."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+MOVER_DIPOLE_ANALYTIC = 0
+MOVER_INTERPOLATED = 1 << 0
+PROJECT_CURRENT = 1 << 1
+SOLVER_FORWARD = 1 << 2
+SOLVER_LEAPFROG = 1 << 3
+UPDATE_BOUNDARIES = 1 << 4
+SKIP_MIGRATION = 1 << 5
+
+# every symbol include/ipic3d_b200.h declares
+API_SYMBOLS = [
+    "ipic_last_error", "ipic_version", "ipic_device_count", "ipic_create", "ipic_create_slab", "ipic_destroy",
+    "ipic_set_headroom", "ipic_comm_unique_id", "ipic_comm_init", "ipic_upload_cells", "ipic_download_cells",
+    "ipic_cell_counts", "ipic_total_particles", "ipic_upload_fields", "ipic_download_fields", "ipic_step",
+    "ipic_step_async", "ipic_sync", "ipic_count_misplaced", "ipic_profile_reset", "ipic_profile_get",
+]
+
+
+class IpicError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("ipic3d_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+class Props(C.Structure):
+    """``ipic_props``: POD mirror of ipic3d::UniverseProperties (reference universe_properties.h:52-75)."""
+    _fields_ = [("size", C.c_int64 * 3), ("cellWidth", C.c_double * 3), ("dt", C.c_double),
+                ("speedOfLight", C.c_double), ("planetRadius", C.c_double), ("objectCenter", C.c_double * 3),
+                ("origin", C.c_double * 3), ("externalMagneticField", C.c_double * 3)]
+
+    @classmethod
+    def make(cls, size, cellWidth=(1.0, 1.0, 1.0), dt=1.0, speedOfLight=1.0, planetRadius=0.0,
+             objectCenter=(0.0, 0.0, 0.0), origin=(0.0, 0.0, 0.0), externalMagneticField=(0.0, 0.0, 0.0)):
+        p = cls()
+        if np.isscalar(size):
+            size = (size,) * 3
+        p.size[:] = [int(s) for s in size]
+        p.cellWidth[:] = cellWidth
+        p.dt, p.speedOfLight, p.planetRadius = dt, speedOfLight, planetRadius
+        p.objectCenter[:] = objectCenter
+        p.origin[:] = origin
+        p.externalMagneticField[:] = externalMagneticField
+        return p
+
+    @classmethod
+    def from_other(cls, other):
+        """Copy from any ctypes structure with the same layout (e.g. the test harness' Props)."""
+        p = cls()
+        assert C.sizeof(other) == C.sizeof(p)
+        C.memmove(C.byref(p), C.byref(other), C.sizeof(p))
+        return p
+
+    @property
+    def ncells(self):
+        return int(self.size[0] * self.size[1] * self.size[2])
+
+    def grid_len(self, extra):
+        return int((self.size[0] + extra) * (self.size[1] + extra) * (self.size[2] + extra))
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", "libipic3d_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Load the CUDA library; fails loudly if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise IpicError(-5, "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(nvcc, sm_100a) first; there is no CPU fallback" % path)
+        lib = C.CDLL(path)
+        lib.ipic_last_error.restype = C.c_char_p
+        lib.ipic_version.restype = C.c_char_p
+        _lib = lib
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _up(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+class Context:
+    """One z-slab of a universe on one GPU (``ipic_ctx``).  Single GPU: rank 0 of 1."""
+
+    def __init__(self, props, device=0, rank=0, nranks=1):
+        self.lib = load_library()
+        self.props = Props.from_other(props)
+        self.rank, self.nranks = rank, nranks
+        self.h = C.c_void_p()
+        self._ck(self.lib.ipic_create_slab(C.byref(self.props), C.c_int(device), C.c_int(rank), C.c_int(nranks), C.byref(self.h)))
+        nz = int(self.props.size[2]) // nranks
+        self.owned_cells = int(self.props.size[0] * self.props.size[1]) * nz
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise IpicError(rc, self.lib.ipic_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ipic_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- multi-GPU wiring --
+    @staticmethod
+    def comm_unique_id():
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.ipic_comm_unique_id(buf)
+        if rc:
+            raise IpicError(rc, lib.ipic_last_error().decode())
+        return buf.raw
+
+    def comm_init(self, unique_id):
+        self._ck(self.lib.ipic_comm_init(self.h, C.c_char_p(unique_id)))
+
+    # -- state --
+    def set_headroom(self, slack, min_pad=64):
+        self._ck(self.lib.ipic_set_headroom(self.h, C.c_double(slack), C.c_int64(min_pad)))
+
+    def upload_cells(self, counts, aos):
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        aos = np.ascontiguousarray(aos, dtype=np.float64).reshape(-1, 8)
+        if counts.size != self.owned_cells or int(counts.sum()) != len(aos):
+            raise ValueError("counts/particles shape mismatch")
+        self._ck(self.lib.ipic_upload_cells(self.h, _up(counts), _dp(aos)))
+
+    def upload_cells_ptr(self, counts, aos_ptr):
+        """Upload from a raw host pointer (e.g. pinned memory owned by the caller)."""
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        self._ck(self.lib.ipic_upload_cells(self.h, _up(counts), C.c_void_p(aos_ptr)))
+
+    def cell_counts(self):
+        out = np.zeros(self.owned_cells, dtype=np.uint64)
+        self._ck(self.lib.ipic_cell_counts(self.h, _up(out)))
+        return out
+
+    def total_particles(self):
+        t = C.c_uint64(0)
+        self._ck(self.lib.ipic_total_particles(self.h, C.byref(t)))
+        return int(t.value)
+
+    def download_cells(self):
+        n = self.total_particles()
+        counts = np.zeros(self.owned_cells, dtype=np.uint64)
+        aos = np.zeros((n, 8), dtype=np.float64)
+        self._ck(self.lib.ipic_download_cells(self.h, _up(counts), _dp(aos), C.c_uint64(n)))
+        return counts, aos
+
+    def download_cells_ptr(self, counts, aos_ptr, capacity):
+        self._ck(self.lib.ipic_download_cells(self.h, _up(counts), C.c_void_p(aos_ptr), C.c_uint64(capacity)))
+
+    def upload_fields(self, field=None, bcfield=None, density=None):
+        f = None if field is None else np.ascontiguousarray(field, dtype=np.float64).reshape(self.props.grid_len(3), 9)
+        b = None if bcfield is None else np.ascontiguousarray(bcfield, dtype=np.float64).reshape(self.props.grid_len(2), 3)
+        j = None if density is None else np.ascontiguousarray(density, dtype=np.float64).reshape(self.props.grid_len(1), 3)
+        self._ck(self.lib.ipic_upload_fields(self.h, _dp(f), _dp(b), _dp(j)))
+
+    def download_fields(self):
+        f = np.zeros((self.props.grid_len(3), 9))
+        b = np.zeros((self.props.grid_len(2), 3))
+        j = np.zeros((self.props.grid_len(1), 3))
+        self._ck(self.lib.ipic_download_fields(self.h, _dp(f), _dp(b), _dp(j)))
+        return f, b, j
+
+    # -- the hot path --
+    def step(self, n=1, flags=0):
+        """Blocking: n iterations of the simulateSteps loop body; returns (firstStep, remainingSteps) seconds."""
+        a, b = C.c_double(0), C.c_double(0)
+        self._ck(self.lib.ipic_step(self.h, C.c_uint64(n), C.c_uint32(flags), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def step_async(self, n=1, flags=0):
+        self._ck(self.lib.ipic_step_async(self.h, C.c_uint64(n), C.c_uint32(flags)))
+
+    def sync(self):
+        self._ck(self.lib.ipic_sync(self.h))
+
+    def count_misplaced(self):
+        t = C.c_uint64(0)
+        self._ck(self.lib.ipic_count_misplaced(self.h, C.byref(t)))
+        return int(t.value)
+
+    def profile_reset(self):
+        self._ck(self.lib.ipic_profile_reset(self.h))
+
+    def profile_get(self):
+        a, b, n = C.c_double(0), C.c_double(0), C.c_uint64(0)
+        self._ck(self.lib.ipic_profile_get(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, int(n.value)

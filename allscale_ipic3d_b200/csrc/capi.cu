@@ -1,0 +1,608 @@
+// C ABI (include/ipic3d_b200.h) over the sm_100a kernels: context, HBM layout, step orchestration.
+//
+// What simulateSteps keeps in locals (TransferBuffers, scratch; reference simulator.h:153-156) lives
+// in ipic_ctx.  The loop body of simulateSteps (simulator.h:181-230) is ipic_step.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/ipic3d_b200.h"
+#include "comm.h"
+#include "field_kernels.h"
+#include "ipic_device.cuh"
+#include "particle_kernels.h"
+
+using namespace ipic;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int code, const char* fmt, ...) {
+	char buf[512];
+	va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+	g_lastError = buf;
+	return code;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(IPIC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+inline int64_t alignUp(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+} // namespace
+
+struct ipic_ctx {
+	int device = 0, rank = 0, nranks = 1;
+	ipic_props props{};
+	Geometry g{};
+	cudaStream_t stream = nullptr;
+
+	// particle storage: two generations with a common layout
+	int64_t slots = 0;
+	ParticleArrays buf[2]{};
+	int cur = 0;                                   // generation holding the live particles
+	std::vector<int64_t> hCellStart;               // ncellsLocal + 1
+	int64_t* dCellStart = nullptr;
+	int* dCount = nullptr;                         // live particles per local cell (head of segment, generation `cur`)
+	int* dStay = nullptr;                          // stayers per cell after the mover (head of segment, other generation)
+	int* dLeave = nullptr;                         // outbox entries per local cell
+	unsigned char* dTag = nullptr;                 // direction tag per slot (outbox entries only)
+	int* dStop = nullptr;                          // [0] stop, [1] first failing step, [2] overflow seen
+	bool haveCells = false;
+	int items = 2;                                 // particles per thread in the mover tile (from the mean population)
+	double slack = 0.25;                           // head-room per cell as a fraction of its population
+	int64_t minPad = 64;                           // ... and in absolute slots
+
+	// fields (always the global grids; replicated per slab)
+	double* dEB = nullptr;                         // (n+3)^3 x 6
+	double* dBext = nullptr;                       // (n+3)^3 x 3
+	double* dBc = nullptr;                         // (n+2)^3 x 3
+	double* dJ = nullptr;                          // (n+1)^3 x 3
+	double* dCellJ = nullptr;                      // global cells x 24
+	int64_t nField = 0, nBc = 0, nJ = 0;
+
+	// staging for AoS transfers
+	double* dStage = nullptr; int64_t stageDoubles = 0;
+	int64_t* dAosStart = nullptr;
+
+	// measurement
+	bool profiling = false;
+	std::vector<cudaEvent_t> events;               // triples: before mover, after mover, after import
+	size_t eventsUsed = 0;
+	double moverMs = 0, importMs = 0;
+	uint64_t launches = 0;
+
+	ipic_comm* comm = nullptr;
+};
+
+namespace {
+
+int ownedCells(const ipic_ctx* c) { return c->g.nx * c->g.ny * c->g.lz; }
+
+void freeParticleBuffers(ipic_ctx* c) {
+	for (int b = 0; b < 2; b++) for (int f = 0; f < kFields; f++) { if (c->buf[b].f[f]) cudaFree(c->buf[b].f[f]); c->buf[b].f[f] = nullptr; }
+	if (c->dTag) cudaFree(c->dTag);
+	c->dTag = nullptr;
+	c->slots = 0;
+}
+
+int allocParticleBuffers(ParticleArrays out[2], unsigned char** tag, int64_t slots) {
+	for (int b = 0; b < 2; b++) for (int f = 0; f < kFields; f++) CK(cudaMalloc(&out[b].f[f], (size_t)std::max<int64_t>(slots, 1) * sizeof(double)));
+	CK(cudaMalloc(tag, (size_t)std::max<int64_t>(slots, 1)));
+	return IPIC_OK;
+}
+
+// capacity of a cell segment that currently needs room for n particles
+int64_t capacityFor(const ipic_ctx* c, int64_t n) {
+	return alignUp(n + std::max<int64_t>((int64_t)std::ceil((double)n * c->slack), c->minPad), kSlotAlign);
+}
+
+// segment layout for the local cell array (owned cells from `need`, ghost cells sized like the
+// largest owned cell of the adjacent plane's average outbox expectation)
+void buildLayout(const ipic_ctx* c, const std::vector<int64_t>& needOwned, std::vector<int64_t>& start) {
+	const Geometry& g = c->g;
+	start.assign((size_t)g.ncellsLocal + 1, 0);
+	int64_t maxOwned = 0;
+	for (int64_t v : needOwned) maxOwned = std::max(maxOwned, v);
+	const int64_t ghostCap = alignUp(std::max<int64_t>(maxOwned / 2, 256), kSlotAlign);
+	int64_t pos = 0;
+	for (int xy = 0; xy < g.nx * g.ny; xy++)
+		for (int zs = 0; zs < g.lzs; zs++) {
+			const int cell = xy * g.lzs + zs;
+			start[cell] = pos;
+			const bool isGhost = g.ghost && (zs == 0 || zs == g.lzs - 1);
+			pos += isGhost ? ghostCap : capacityFor(c, needOwned[(size_t)xy * g.lz + (zs - g.ghost)]);
+		}
+	start[(size_t)g.ncellsLocal] = pos;
+}
+
+int ensureStage(ipic_ctx* c, int64_t doubles) {
+	if (c->stageDoubles >= doubles) return IPIC_OK;
+	if (c->dStage) cudaFree(c->dStage);
+	c->dStage = nullptr; c->stageDoubles = 0;
+	CK(cudaMalloc(&c->dStage, (size_t)std::max<int64_t>(doubles, 1) * sizeof(double)));
+	c->stageDoubles = doubles;
+	return IPIC_OK;
+}
+
+int fetchOwnedCounts(ipic_ctx* c, const int* dArray, std::vector<int>& out) {
+	std::vector<int> local((size_t)c->g.ncellsLocal);
+	CK(cudaMemcpyAsync(local.data(), dArray, local.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	out.resize((size_t)ownedCells(c));
+	for (int xy = 0; xy < c->g.nx * c->g.ny; xy++)
+		for (int zl = 0; zl < c->g.lz; zl++) out[(size_t)xy * c->g.lz + zl] = local[(size_t)xy * c->g.lzs + zl + c->g.ghost];
+	return IPIC_OK;
+}
+
+void fillGeometry(ipic_ctx* c) {
+	const ipic_props& p = c->props;
+	Geometry& g = c->g;
+	g.nx = (int)p.size[0]; g.ny = (int)p.size[1]; g.nz = (int)p.size[2];
+	g.lz = g.nz / c->nranks;
+	g.z0 = c->rank * g.lz;
+	g.ghost = c->nranks > 1 ? 1 : 0;
+	g.lzs = g.lz + 2 * g.ghost;
+	g.ncellsLocal = g.nx * g.ny * g.lzs;
+	for (int a = 0; a < 3; a++) {
+		g.w[a] = p.cellWidth[a];
+		g.hw[a] = p.cellWidth[a] / 2.0;
+		g.origin[a] = p.origin[a];
+		g.objectCenter[a] = p.objectCenter[a];
+	}
+	g.dt = p.dt;
+	g.c = p.speedOfLight;
+	g.planetRadius = p.planetRadius;
+	g.r2planet = p.planetRadius * p.planetRadius;
+	g.magTemp = -p.externalMagneticField[2] * std::pow(p.planetRadius, 3);   // host libm, as the reference (cell.h:919)
+	g.pic = M_PI * p.speedOfLight;                                           // cell.h:949
+	g.vol = p.cellWidth[0] * p.cellWidth[1] * p.cellWidth[2];
+}
+
+int pickItems(const ipic_ctx* c, int64_t total) {
+	const int64_t cells = std::max(1, ownedCells(c));
+	const int64_t avg = total / cells;
+	return avg >= 640 ? 4 : (avg >= 192 ? 2 : 1);
+}
+
+cudaEvent_t nextEvent(ipic_ctx* c) {
+	if (c->eventsUsed == c->events.size()) { cudaEvent_t e; cudaEventCreate(&e); c->events.push_back(e); }
+	return c->events[c->eventsUsed++];
+}
+
+int drainProfile(ipic_ctx* c) {
+	for (size_t i = 0; i + 2 < c->eventsUsed; i += 3) {
+		float a = 0, b = 0;
+		CK(cudaEventElapsedTime(&a, c->events[i], c->events[i + 1]));
+		CK(cudaEventElapsedTime(&b, c->events[i + 1], c->events[i + 2]));
+		c->moverMs += a; c->importMs += b;
+	}
+	c->eventsUsed = 0;
+	return IPIC_OK;
+}
+
+// Re-establish a valid layout after the import of `failedStep` ran out of room: the generation that
+// was being written still holds every stayer (head) and every outbox (tail) intact, dCount holds the
+// size every cell needs.  Build a roomier layout, move the heads over and redo that import.
+int relayoutAfterOverflow(ipic_ctx* c, int outGen, int failedStep) {
+	std::vector<int> need;
+	int rc = fetchOwnedCounts(c, c->dCount, need);
+	if (rc) return rc;
+	std::vector<int64_t> need64(need.begin(), need.end());
+	std::vector<int64_t> newStart;
+	c->slack = std::min(c->slack * 1.5 + 0.1, 4.0);
+	buildLayout(c, need64, newStart);
+	ParticleArrays nb[2]{}; unsigned char* ntag = nullptr;
+	const int64_t nslots = newStart.back();
+	rc = allocParticleBuffers(nb, &ntag, nslots);
+	if (rc) return rc;
+	int64_t* dNewStart = nullptr;
+	CK(cudaMalloc(&dNewStart, newStart.size() * sizeof(int64_t)));
+	CK(cudaMemcpyAsync(dNewStart, newStart.data(), newStart.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemsetAsync(c->dStop, 0, 3 * sizeof(int), c->stream));
+	int big = 0x7fffffff;
+	CK(cudaMemcpyAsync(c->dStop + 1, &big, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+	launch_copy_heads(c->g, c->buf[outGen], c->dCellStart, nb[outGen], dNewStart, c->dStay, c->stream);
+	ImportArgs ia{};
+	ia.g = c->g; ia.src = c->buf[outGen]; ia.srcStart = c->dCellStart; ia.srcLeave = c->dLeave; ia.tag = c->dTag;
+	ia.dst = nb[outGen]; ia.dstStart = dNewStart; ia.stay = c->dStay; ia.dstCount = c->dCount;
+	ia.reserveOwnOutbox = 0; ia.stopFlag = c->dStop; ia.stepIndex = failedStep; ia.zBegin = 0; ia.zCount = c->g.lz;
+	launch_import(ia, c->stream);
+	c->launches += 3;
+	CK(cudaStreamSynchronize(c->stream));
+	int stop[3];
+	CK(cudaMemcpy(stop, c->dStop, sizeof stop, cudaMemcpyDeviceToHost));
+	// swap in the new storage
+	freeParticleBuffers(c);
+	cudaFree(c->dCellStart);
+	c->buf[0] = nb[0]; c->buf[1] = nb[1]; c->dTag = ntag; c->dCellStart = dNewStart; c->slots = nslots; c->hCellStart = newStart;
+	if (stop[0]) return fail(IPIC_ERR_INTERNAL, "relayout did not resolve the overflow of step %d", failedStep);
+	return IPIC_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* ipic_last_error(void) { return g_lastError.c_str(); }
+const char* ipic_version(void) { return "ipic3d_b200 0.1 (sm_100a)"; }
+
+int ipic_device_count(int* count) {
+	if (!count) return fail(IPIC_ERR_ARG, "count is null");
+	CK(cudaGetDeviceCount(count));
+	return IPIC_OK;
+}
+
+int ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, ipic_ctx** out) {
+	if (!props || !out) return fail(IPIC_ERR_ARG, "null argument");
+	if (nranks < 1 || rank < 0 || rank >= nranks) return fail(IPIC_ERR_ARG, "bad rank %d of %d", rank, nranks);
+	for (int a = 0; a < 3; a++) {
+		if (props->size[a] <= 0 || props->size[a] > (1 << 20)) return fail(IPIC_ERR_ARG, "bad grid size");
+		if (!(props->cellWidth[a] > 0)) return fail(IPIC_ERR_ARG, "cell width must be positive");
+	}
+	if (props->size[2] % nranks != 0) return fail(IPIC_ERR_ARG, "nz=%lld is not divisible by %d slabs", (long long)props->size[2], nranks);
+	if (!(props->dt > 0) || !(props->speedOfLight > 0) || !(props->planetRadius >= 0)) return fail(IPIC_ERR_ARG, "dt, speedOfLight must be positive and planetRadius non-negative");
+	int ndev = 0;
+	CK(cudaGetDeviceCount(&ndev));
+	if (device < 0 || device >= ndev) return fail(IPIC_ERR_CUDA, "CUDA device %d not available (%d devices)", device, ndev);
+	CK(cudaSetDevice(device));
+	ipic_ctx* c = new ipic_ctx();
+	c->device = device; c->rank = rank; c->nranks = nranks; c->props = *props;
+	fillGeometry(c);
+	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	const Geometry& g = c->g;
+	CK(cudaMalloc(&c->dCellStart, ((size_t)g.ncellsLocal + 1) * sizeof(int64_t)));
+	CK(cudaMalloc(&c->dCount, (size_t)g.ncellsLocal * sizeof(int)));
+	CK(cudaMalloc(&c->dStay, (size_t)g.ncellsLocal * sizeof(int)));
+	CK(cudaMalloc(&c->dLeave, (size_t)g.ncellsLocal * sizeof(int)));
+	CK(cudaMemset(c->dCount, 0, (size_t)g.ncellsLocal * sizeof(int)));
+	CK(cudaMemset(c->dStay, 0, (size_t)g.ncellsLocal * sizeof(int)));
+	CK(cudaMemset(c->dLeave, 0, (size_t)g.ncellsLocal * sizeof(int)));
+	CK(cudaMalloc(&c->dStop, 3 * sizeof(int)));
+	int stop[3] = { 0, 0x7fffffff, 0 };
+	CK(cudaMemcpy(c->dStop, stop, sizeof stop, cudaMemcpyHostToDevice));
+	c->nField = (int64_t)(g.nx + 3) * (g.ny + 3) * (g.nz + 3);
+	c->nBc = (int64_t)(g.nx + 2) * (g.ny + 2) * (g.nz + 2);
+	c->nJ = (int64_t)(g.nx + 1) * (g.ny + 1) * (g.nz + 1);
+	CK(cudaMalloc(&c->dEB, (size_t)c->nField * 6 * sizeof(double)));
+	CK(cudaMalloc(&c->dBext, (size_t)c->nField * 3 * sizeof(double)));
+	CK(cudaMalloc(&c->dBc, (size_t)c->nBc * 3 * sizeof(double)));
+	CK(cudaMalloc(&c->dJ, (size_t)c->nJ * 3 * sizeof(double)));
+	CK(cudaMalloc(&c->dCellJ, (size_t)g.nx * g.ny * g.nz * 24 * sizeof(double)));
+	CK(cudaMemset(c->dEB, 0, (size_t)c->nField * 6 * sizeof(double)));
+	CK(cudaMemset(c->dBext, 0, (size_t)c->nField * 3 * sizeof(double)));
+	CK(cudaMemset(c->dBc, 0, (size_t)c->nBc * 3 * sizeof(double)));
+	CK(cudaMemset(c->dJ, 0, (size_t)c->nJ * 3 * sizeof(double)));
+	CK(cudaMemset(c->dCellJ, 0, (size_t)g.nx * g.ny * g.nz * 24 * sizeof(double)));
+	CK(cudaMalloc(&c->dAosStart, ((size_t)ownedCells(c) + 1) * sizeof(int64_t)));
+	*out = c;
+	return IPIC_OK;
+}
+
+int ipic_create(const ipic_props* props, int device, ipic_ctx** out) { return ipic_create_slab(props, device, 0, 1, out); }
+
+int ipic_destroy(ipic_ctx* c) {
+	if (!c) return IPIC_OK;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->comm) comm_destroy(c->comm);
+	freeParticleBuffers(c);
+	cudaFree(c->dCellStart); cudaFree(c->dCount); cudaFree(c->dStay); cudaFree(c->dLeave); cudaFree(c->dStop);
+	cudaFree(c->dEB); cudaFree(c->dBext); cudaFree(c->dBc); cudaFree(c->dJ); cudaFree(c->dCellJ);
+	cudaFree(c->dStage); cudaFree(c->dAosStart);
+	for (auto e : c->events) cudaEventDestroy(e);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+	return IPIC_OK;
+}
+
+int ipic_set_headroom(ipic_ctx* c, double slack, int64_t minPad) {
+	if (!c || !(slack >= 0) || minPad < 0) return fail(IPIC_ERR_ARG, "bad head-room");
+	c->slack = slack; c->minPad = minPad;
+	return IPIC_OK;
+}
+
+int ipic_upload_cells(ipic_ctx* c, const uint64_t* counts, const double* aos) {
+	if (!c || !counts) return fail(IPIC_ERR_ARG, "null argument");
+	CK(cudaSetDevice(c->device));
+	const int nOwned = ownedCells(c);
+	std::vector<int64_t> need((size_t)nOwned), aosStart((size_t)nOwned + 1, 0);
+	std::vector<int> localCount((size_t)c->g.ncellsLocal, 0);
+	for (int i = 0; i < nOwned; i++) {
+		if (counts[i] > 0x3fffffffu) return fail(IPIC_ERR_ARG, "cell %d holds %llu particles (limit 2^30 per cell)", i, (unsigned long long)counts[i]);
+		need[i] = (int64_t)counts[i];
+		aosStart[i + 1] = aosStart[i] + need[i];
+		const int xy = i / c->g.lz, zl = i % c->g.lz;
+		localCount[(size_t)xy * c->g.lzs + zl + c->g.ghost] = (int)counts[i];
+	}
+	const int64_t total = aosStart[nOwned];
+	if (total > 0 && !aos) return fail(IPIC_ERR_ARG, "particles_aos is null");
+	std::vector<int64_t> start;
+	buildLayout(c, need, start);
+	if (start.back() > c->slots || start.back() < c->slots / 2) {
+		freeParticleBuffers(c);
+		int rc = allocParticleBuffers(c->buf, &c->dTag, start.back());
+		if (rc) return rc;
+		c->slots = start.back();
+	}
+	c->hCellStart = start;
+	CK(cudaMemcpyAsync(c->dCellStart, start.data(), start.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->dAosStart, aosStart.data(), aosStart.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->dCount, localCount.data(), localCount.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemsetAsync(c->dLeave, 0, (size_t)c->g.ncellsLocal * sizeof(int), c->stream));
+	int rc = ensureStage(c, total * 8);
+	if (rc) return rc;
+	if (total) {
+		CK(cudaMemcpyAsync(c->dStage, aos, (size_t)total * 64, cudaMemcpyHostToDevice, c->stream));
+		launch_scatter_aos(c->g, c->dStage, c->dAosStart, c->buf[c->cur], c->dCellStart, c->stream);
+		c->launches++;
+	}
+	CK(cudaStreamSynchronize(c->stream));     // host vectors above go out of scope
+	c->haveCells = true;
+	c->items = pickItems(c, total);
+	return IPIC_OK;
+}
+
+int ipic_cell_counts(ipic_ctx* c, uint64_t* counts) {
+	if (!c || !counts) return fail(IPIC_ERR_ARG, "null argument");
+	CK(cudaSetDevice(c->device));
+	std::vector<int> owned;
+	int rc = fetchOwnedCounts(c, c->dCount, owned);
+	if (rc) return rc;
+	for (size_t i = 0; i < owned.size(); i++) counts[i] = (uint64_t)owned[i];
+	return IPIC_OK;
+}
+
+int ipic_total_particles(ipic_ctx* c, uint64_t* total) {
+	if (!c || !total) return fail(IPIC_ERR_ARG, "null argument");
+	std::vector<uint64_t> counts((size_t)ownedCells(c));
+	int rc = ipic_cell_counts(c, counts.data());
+	if (rc) return rc;
+	uint64_t t = 0; for (uint64_t v : counts) t += v;
+	*total = t;
+	return IPIC_OK;
+}
+
+int ipic_download_cells(ipic_ctx* c, uint64_t* counts, double* aos, uint64_t capacity) {
+	if (!c || !counts) return fail(IPIC_ERR_ARG, "null argument");
+	CK(cudaSetDevice(c->device));
+	std::vector<int> owned;
+	int rc = fetchOwnedCounts(c, c->dCount, owned);
+	if (rc) return rc;
+	std::vector<int64_t> aosStart(owned.size() + 1, 0);
+	for (size_t i = 0; i < owned.size(); i++) { counts[i] = (uint64_t)owned[i]; aosStart[i + 1] = aosStart[i] + owned[i]; }
+	const int64_t total = aosStart.back();
+	if ((uint64_t)total > capacity) return fail(IPIC_ERR_CAPACITY, "download needs room for %lld particles, caller offers %llu", (long long)total, (unsigned long long)capacity);
+	if (total == 0) return IPIC_OK;
+	if (!aos) return fail(IPIC_ERR_ARG, "particles_aos is null");
+	rc = ensureStage(c, total * 8);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(c->dAosStart, aosStart.data(), aosStart.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+	launch_gather_aos(c->g, c->dStage, c->dAosStart, c->buf[c->cur], c->dCellStart, c->stream);
+	c->launches++;
+	CK(cudaMemcpyAsync(aos, c->dStage, (size_t)total * 64, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return IPIC_OK;
+}
+
+int ipic_upload_fields(ipic_ctx* c, const double* field, const double* bc, const double* J) {
+	if (!c) return fail(IPIC_ERR_ARG, "null context");
+	CK(cudaSetDevice(c->device));
+	if (field) {
+		int rc = ensureStage(c, c->nField * 9);
+		if (rc) return rc;
+		CK(cudaMemcpyAsync(c->dStage, field, (size_t)c->nField * 72, cudaMemcpyHostToDevice, c->stream));
+		launch_split_field(c->dStage, c->dEB, c->dBext, c->nField, c->stream);
+		c->launches++;
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	if (bc) CK(cudaMemcpy(c->dBc, bc, (size_t)c->nBc * 24, cudaMemcpyHostToDevice));
+	if (J) CK(cudaMemcpy(c->dJ, J, (size_t)c->nJ * 24, cudaMemcpyHostToDevice));
+	return IPIC_OK;
+}
+
+int ipic_download_fields(ipic_ctx* c, double* field, double* bc, double* J) {
+	if (!c) return fail(IPIC_ERR_ARG, "null context");
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	if (field) {
+		int rc = ensureStage(c, c->nField * 9);
+		if (rc) return rc;
+		launch_merge_field(c->dStage, c->dEB, c->dBext, c->nField, c->stream);
+		c->launches++;
+		CK(cudaMemcpyAsync(field, c->dStage, (size_t)c->nField * 72, cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	if (bc) CK(cudaMemcpy(bc, c->dBc, (size_t)c->nBc * 24, cudaMemcpyDeviceToHost));
+	if (J) CK(cudaMemcpy(J, c->dJ, (size_t)c->nJ * 24, cudaMemcpyDeviceToHost));
+	return IPIC_OK;
+}
+
+// One iteration of the time loop, enqueued on the context's stream.
+static int enqueueStep(ipic_ctx* c, uint32_t flags, int stepIndex) {
+	const int items = c->items;
+	const bool interp = flags & IPIC_MOVER_INTERPOLATED;
+	const bool project = flags & IPIC_PROJECT_CURRENT;
+	const bool solve = flags & (IPIC_SOLVER_FORWARD | IPIC_SOLVER_LEAPFROG);
+	const bool migrate = !(flags & IPIC_SKIP_MIGRATION);
+	const int in = c->cur, out = c->cur ^ 1;
+
+	MoveArgs ma{};
+	ma.g = c->g; ma.in = c->buf[in]; ma.out = c->buf[out]; ma.cellStart = c->dCellStart;
+	ma.countIn = c->dCount; ma.countOut = c->dStay; ma.nLeave = c->dLeave; ma.tag = c->dTag;
+	ma.fieldEB = c->dEB; ma.cellJ = c->dCellJ; ma.stopFlag = c->dStop;
+	ma.zBegin = 0; ma.zCount = c->g.lz; ma.itemsPerThread = items;
+	ma.interpolate = interp; ma.migrate = migrate; ma.push = true;
+
+	auto fieldPhase = [&]() {
+		if (flags & IPIC_UPDATE_BOUNDARIES) { launch_update_boundaries(c->g, c->dEB, c->dBext, c->dBc, c->dStop, c->stream); c->launches += 2; }
+		if (solve) c->launches += launch_field_solver(c->g, (flags & IPIC_SOLVER_FORWARD) != 0, c->dEB, c->dBc, c->dJ, c->dStop, c->stream);
+	};
+
+	// The reference order is project -> boundaries/solve -> move -> import (simulator.h:189-223).  The
+	// analytic mover never reads the grid, so there the projection is fused into the mover pass and the
+	// field phase runs after it with identical results; the interpolating mover needs the new fields
+	// first, so its projection is a separate read-only pass.
+	const bool fuseDeposit = project && !interp;
+	if (project && interp) {
+		MoveArgs da = ma; da.push = false; da.deposit = true; da.interpolate = false;
+		launch_move(da, c->stream);
+		launch_gather_current(c->g, c->dCellJ, c->dJ, c->dStop, c->stream);
+		c->launches += 2;
+	}
+	if (!fuseDeposit) fieldPhase();
+
+	cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+	if (c->profiling) { e0 = nextEvent(c); e1 = nextEvent(c); e2 = nextEvent(c); cudaEventRecord(e0, c->stream); }
+	ma.deposit = fuseDeposit;
+	launch_move(ma, c->stream);
+	c->launches++;
+	if (c->profiling) cudaEventRecord(e1, c->stream);
+
+	if (fuseDeposit) {
+		launch_gather_current(c->g, c->dCellJ, c->dJ, c->dStop, c->stream);
+		c->launches++;
+		fieldPhase();
+	}
+
+	if (migrate) {
+		ImportArgs ia{};
+		ia.g = c->g; ia.src = c->buf[out]; ia.srcStart = c->dCellStart; ia.srcLeave = c->dLeave; ia.tag = c->dTag;
+		ia.dst = c->buf[out]; ia.dstStart = c->dCellStart; ia.stay = c->dStay; ia.dstCount = c->dCount;
+		ia.reserveOwnOutbox = 1; ia.stopFlag = c->dStop; ia.stepIndex = stepIndex; ia.zBegin = 0; ia.zCount = c->g.lz;
+		launch_import(ia, c->stream);
+		c->launches += 2;
+	} else {
+		CK(cudaMemcpyAsync(c->dCount, c->dStay, (size_t)c->g.ncellsLocal * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+	}
+	if (c->profiling) cudaEventRecord(e2, c->stream);
+	c->cur = out;
+	CK(cudaGetLastError());
+	return IPIC_OK;
+}
+
+static int enqueueSteps(ipic_ctx* c, uint64_t first, uint64_t count, uint32_t flags) {
+	for (uint64_t s = first; s < first + count; s++) {
+		int rc = enqueueStep(c, flags, (int)std::min<uint64_t>(s, 0x7ffffff0u));
+		if (rc) return rc;
+	}
+	return IPIC_OK;
+}
+
+static int checkStepArgs(ipic_ctx* c, uint32_t flags) {
+	if (!c) return fail(IPIC_ERR_ARG, "null context");
+	if (!c->haveCells) return fail(IPIC_ERR_ARG, "ipic_upload_cells has not been called");
+	if ((flags & IPIC_SOLVER_FORWARD) && (flags & IPIC_SOLVER_LEAPFROG)) return fail(IPIC_ERR_ARG, "choose one field solver");
+	if ((flags & IPIC_UPDATE_BOUNDARIES) && !(c->g.nx == c->g.ny && c->g.ny == c->g.nz)) return fail(IPIC_ERR_ARG, "updateFieldsOnBoundaries assumes a cubic universe (reference field.h:422)");
+	if (c->nranks > 1 && !c->comm) return fail(IPIC_ERR_COMM, "slab context %d/%d has no communicator (ipic_comm_init)", c->rank, c->nranks);
+	return IPIC_OK;
+}
+
+int ipic_step_async(ipic_ctx* c, uint64_t numSteps, uint32_t flags) {
+	int rc = checkStepArgs(c, flags);
+	if (rc) return rc;
+	CK(cudaSetDevice(c->device));
+	return enqueueSteps(c, 0, numSteps, flags);
+}
+
+int ipic_sync(ipic_ctx* c) {
+	if (!c) return fail(IPIC_ERR_ARG, "null context");
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	return IPIC_OK;
+}
+
+int ipic_step(ipic_ctx* c, uint64_t numSteps, uint32_t flags, double* tFirst, double* tRest) {
+	if (tFirst) *tFirst = 0;
+	if (tRest) *tRest = 0;
+	{ int rc = checkStepArgs(c, flags); if (rc) return rc; }
+	if (numSteps == 0) return IPIC_OK;
+	CK(cudaSetDevice(c->device));
+	cudaEvent_t ev[3];
+	for (auto& e : ev) CK(cudaEventCreate(&e));
+	uint64_t done = 0;
+	float msFirst = 0, msRest = 0;
+	while (done < numSteps) {
+		const int genAtStart = c->cur;
+		const uint64_t batch = numSteps - done;
+		CK(cudaEventRecord(ev[0], c->stream));
+		int rc = enqueueSteps(c, 0, 1, flags);
+		if (rc) return rc;
+		CK(cudaEventRecord(ev[1], c->stream));
+		// the remaining steps carry their index within this batch so that an overflow can be located
+		rc = enqueueSteps(c, 1, batch - 1, flags);
+		if (rc) return rc;
+		CK(cudaEventRecord(ev[2], c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		float a = 0, b = 0;
+		CK(cudaEventElapsedTime(&a, ev[0], ev[1]));
+		CK(cudaEventElapsedTime(&b, ev[1], ev[2]));
+		if (done == 0) { msFirst += a; msRest += b; } else { msRest += a + b; }
+		if (c->profiling) { rc = drainProfile(c); if (rc) return rc; }
+		int stop[3];
+		CK(cudaMemcpy(stop, c->dStop, sizeof stop, cudaMemcpyDeviceToHost));
+		if (!stop[0]) { done = numSteps; break; }
+		// import of step `stop[1]` of this batch overflowed; later steps were skipped on the device
+		const int failed = stop[1];
+		const int outGen = genAtStart ^ ((failed + 1) & 1);
+		if (c->nranks > 1) return fail(IPIC_ERR_CAPACITY, "cell segment overflow in a multi-GPU run (step %d): raise the head-room with ipic_set_headroom", failed);
+		rc = relayoutAfterOverflow(c, outGen, failed);
+		if (rc) return rc;
+		c->cur = outGen;
+		done += (uint64_t)failed + 1;
+	}
+	for (auto& e : ev) cudaEventDestroy(e);
+	if (tFirst) *tFirst = msFirst / 1000.0;
+	if (tRest) *tRest = msRest / 1000.0;
+	return IPIC_OK;
+}
+
+int ipic_count_misplaced(ipic_ctx* c, uint64_t* misplaced) {
+	if (!c || !misplaced) return fail(IPIC_ERR_ARG, "null argument");
+	CK(cudaSetDevice(c->device));
+	unsigned long long* d = nullptr;
+	CK(cudaMalloc(&d, sizeof(unsigned long long)));
+	CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), c->stream));
+	launch_count_misplaced(c->g, c->buf[c->cur], c->dCellStart, c->dCount, d, c->stream);
+	c->launches++;
+	unsigned long long h = 0;
+	CK(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	cudaFree(d);
+	*misplaced = h;
+	return IPIC_OK;
+}
+
+int ipic_profile_reset(ipic_ctx* c) {
+	if (!c) return fail(IPIC_ERR_ARG, "null context");
+	c->profiling = true; c->moverMs = 0; c->importMs = 0; c->launches = 0; c->eventsUsed = 0;
+	return IPIC_OK;
+}
+
+int ipic_profile_get(ipic_ctx* c, double* moverMs, double* importMs, uint64_t* launches) {
+	if (!c) return fail(IPIC_ERR_ARG, "null context");
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	int rc = drainProfile(c);
+	if (rc) return rc;
+	if (moverMs) *moverMs = c->moverMs;
+	if (importMs) *importMs = c->importMs;
+	if (launches) *launches = c->launches;
+	return IPIC_OK;
+}
+
+int ipic_comm_unique_id(void* id128) { return comm_unique_id(id128, g_lastError); }
+
+int ipic_comm_init(ipic_ctx* c, const void* id128) {
+	if (!c || !id128) return fail(IPIC_ERR_ARG, "null argument");
+	CK(cudaSetDevice(c->device));
+	return comm_create(&c->comm, id128, c->rank, c->nranks, g_lastError);
+}
+
+} // extern "C"

@@ -1,0 +1,41 @@
+// Host-side launch interface of particle_kernels.cu.
+#pragma once
+#include "ipic_device.cuh"
+
+namespace ipic {
+
+struct MoveArgs {
+	Geometry g;
+	ParticleArrays in, out;
+	const int64_t* cellStart;
+	const int* countIn;
+	int* countOut;             // number of stayers per cell (head of the segment in `out`)
+	int* nLeave;
+	unsigned char* tag;
+	const double* fieldEB;     // (n+3)^3 x 6 : E.xyz B.xyz per node (mode "interpolated")
+	double* cellJ;             // cells x 24 corner sums (deposit)
+	const int* stopFlag;
+	int zBegin, zCount;        // owned z-planes [zBegin, zBegin+zCount) of the slab
+	int itemsPerThread;
+	bool interpolate, deposit, migrate, push;   // push=false: deposit-only pass (no write-back)
+};
+
+struct ImportArgs {
+	Geometry g;
+	ParticleArrays src; const int64_t* srcStart; const int* srcLeave; const unsigned char* tag;
+	ParticleArrays dst; const int64_t* dstStart; const int* stay; int* dstCount;
+	int reserveOwnOutbox;      // 1 while other cells may still read this cell's outbox out of `dst`
+	int* stopFlag;             // [0] stop, [1] first failing step, [2] overflow seen in this pass
+	int stepIndex;
+	int zBegin, zCount;
+};
+
+void launch_move(const MoveArgs& a, cudaStream_t st);
+void launch_import(const ImportArgs& a, cudaStream_t st);
+void launch_gather_current(const Geometry& g, const double* cellJ, double* J, const int* stopFlag, cudaStream_t st);
+void launch_count_misplaced(const Geometry& g, const ParticleArrays& p, const int64_t* cellStart, const int* count, unsigned long long* bad, cudaStream_t st);
+void launch_scatter_aos(const Geometry& g, const double* aos, const int64_t* aosStart, const ParticleArrays& p, const int64_t* cellStart, cudaStream_t st);
+void launch_gather_aos(const Geometry& g, double* aos, const int64_t* aosStart, const ParticleArrays& p, const int64_t* cellStart, cudaStream_t st);
+void launch_copy_heads(const Geometry& g, const ParticleArrays& src, const int64_t* srcStart, const ParticleArrays& dst, const int64_t* dstStart, const int* count, cudaStream_t st);
+
+} // namespace ipic

@@ -25,6 +25,12 @@
 
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#  define IPIC_API __attribute__((visibility("default")))
+#else
+#  define IPIC_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -64,49 +70,53 @@ enum {
 typedef struct ipic_ctx ipic_ctx;
 
 /* Library / device ------------------------------------------------------------------------- */
-const char* ipic_last_error(void);
-const char* ipic_version(void);
-int  ipic_device_count(int* count);
+IPIC_API const char* ipic_last_error(void);
+IPIC_API const char* ipic_version(void);
+IPIC_API int  ipic_device_count(int* count);
 
 /* Context: one z-slab of the universe on one GPU.  For a single GPU the slab is the whole
  * universe (rank 0 of 1).  Replaces the locals of simulateSteps (TransferBuffers, scratch;
  * simulator.h:153-156). `device` is a CUDA ordinal. */
-int  ipic_create(const ipic_props* props, int device, ipic_ctx** out);
-int  ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, ipic_ctx** out);
-int  ipic_destroy(ipic_ctx* ctx);
+IPIC_API int  ipic_create(const ipic_props* props, int device, ipic_ctx** out);
+IPIC_API int  ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, ipic_ctx** out);
+IPIC_API int  ipic_destroy(ipic_ctx* ctx);
+
+/* Head-room of a cell's segment in HBM: room for n*(1+slack) particles, at least n+min_pad.  When an
+ * import still overflows a segment, single-GPU contexts re-layout transparently. */
+IPIC_API int  ipic_set_headroom(ipic_ctx* ctx, double slack, int64_t min_pad);
 
 /* Multi-GPU wiring (z-slab neighbours, NCCL send/recv).  unique_id is NCCL's 128-byte id,
  * produced on rank 0 by ipic_comm_unique_id and distributed by the caller. */
-int  ipic_comm_unique_id(void* unique_id_128);
-int  ipic_comm_init(ipic_ctx* ctx, const void* unique_id_128);
+IPIC_API int  ipic_comm_unique_id(void* unique_id_128);
+IPIC_API int  ipic_comm_init(ipic_ctx* ctx, const void* unique_id_128);
 
 /* State transfer.  Replaces direct access to universe.cells / .field / .bcfield / .currentDensity
  * (universe.h:12-27).  `counts` has one entry per cell of the GLOBAL grid when the context is the
  * whole universe, or of the slab (nx*ny*nz_local, same flatten) for slab contexts. */
-int  ipic_upload_cells(ipic_ctx* ctx, const uint64_t* counts, const double* particles_aos);
-int  ipic_download_cells(ipic_ctx* ctx, uint64_t* counts, double* particles_aos, uint64_t capacity_particles);
-int  ipic_cell_counts(ipic_ctx* ctx, uint64_t* counts);
-int  ipic_total_particles(ipic_ctx* ctx, uint64_t* total);
-int  ipic_upload_fields(ipic_ctx* ctx, const double* field, const double* bcfield, const double* density);
-int  ipic_download_fields(ipic_ctx* ctx, double* field, double* bcfield, double* density);
+IPIC_API int  ipic_upload_cells(ipic_ctx* ctx, const uint64_t* counts, const double* particles_aos);
+IPIC_API int  ipic_download_cells(ipic_ctx* ctx, uint64_t* counts, double* particles_aos, uint64_t capacity_particles);
+IPIC_API int  ipic_cell_counts(ipic_ctx* ctx, uint64_t* counts);
+IPIC_API int  ipic_total_particles(ipic_ctx* ctx, uint64_t* total);
+IPIC_API int  ipic_upload_fields(ipic_ctx* ctx, const double* field, const double* bcfield, const double* density);
+IPIC_API int  ipic_download_fields(ipic_ctx* ctx, double* field, double* bcfield, double* density);
 
 /* The hot path: numSteps iterations of the loop body of simulateSteps (simulator.h:181-230).
  * Blocking; returns after the device is idle.  t_first / t_rest (seconds, may be NULL) mirror
  * DurationMeasurement{firstStep, remainingSteps} (simulator.h:37-40). */
-int  ipic_step(ipic_ctx* ctx, uint64_t num_steps, uint32_t flags, double* t_first, double* t_rest);
+IPIC_API int  ipic_step(ipic_ctx* ctx, uint64_t num_steps, uint32_t flags, double* t_first, double* t_rest);
 
 /* Same, but only enqueues the work on the context's stream(s); pair with ipic_sync. */
-int  ipic_step_async(ipic_ctx* ctx, uint64_t num_steps, uint32_t flags);
-int  ipic_sync(ipic_ctx* ctx);
+IPIC_API int  ipic_step_async(ipic_ctx* ctx, uint64_t num_steps, uint32_t flags);
+IPIC_API int  ipic_sync(ipic_ctx* ctx);
 
 /* Invariant check mirroring verifyCorrectParticlesPositionInCell (cell.h:1168-1184): number of
  * particles outside the closed box of their cell. */
-int  ipic_count_misplaced(ipic_ctx* ctx, uint64_t* misplaced);
+IPIC_API int  ipic_count_misplaced(ipic_ctx* ctx, uint64_t* misplaced);
 
 /* Measurement support: device time (ms) of the mover / import kernels accumulated since the last
  * reset, and the number of kernel launches issued. */
-int  ipic_profile_reset(ipic_ctx* ctx);
-int  ipic_profile_get(ipic_ctx* ctx, double* mover_ms, double* import_ms, uint64_t* launches);
+IPIC_API int  ipic_profile_reset(ipic_ctx* ctx);
+IPIC_API int  ipic_profile_get(ipic_ctx* ctx, double* mover_ms, double* import_ms, uint64_t* launches);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,57 @@
+"""CPU-side checks of the product boundary: the C-ABI library is built in-tree, exports every symbol that
+include/ipic3d_b200.h declares, and fails loudly (no fallback) when no CUDA device is present."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import allscale_ipic3d_b200 as ipic
+from allscale_ipic3d_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "ipic3d_b200.h")).read()
+    return sorted(set(re.findall(r"IPIC_API\s+[\w\s\*]+?\b(ipic_\w+)\s*\(", text)))
+
+
+def test_library_is_in_tree_and_loads():
+    assert os.path.exists(ipic.lib_path()), "run __graft_entry__.build() first"
+    lib = ipic.load_library()
+    assert b"sm_100a" in lib.ipic_version()
+
+
+def test_every_declared_symbol_is_exported():
+    lib = ipic.load_library()
+    declared = header_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), "%s declared in include/ipic3d_b200.h but not exported" % name
+    assert sorted(capi.API_SYMBOLS) == declared
+
+
+def test_props_layout_matches_header():
+    # 3*int64 + 3*double + 3 doubles + 3*3 doubles
+    assert ctypes.sizeof(ipic.Props) == 8 * (3 + 3 + 3 + 9)
+
+
+def test_product_never_touches_the_oracle():
+    """The shipped package must not import, link or dlopen anything under oracle/."""
+    pkg = os.path.join(ROOT, "allscale_ipic3d_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp", ".hpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.replace("no CPU fallback", "").lower() or f == "__init__.py" and "oracle/" not in text, \
+                    "%s mentions the oracle" % os.path.join(dirpath, f)
+
+
+def test_no_cuda_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(ipic.IpicError) as e:
+        ipic.Context(ipic.Props.make(4))
+    assert e.value.code == -2
