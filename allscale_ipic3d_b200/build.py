@@ -18,9 +18,24 @@ def needs_build(out):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+HOST_SRC = os.path.join(HERE, "..", "host", "src", "host_capi.cc")
+
+
+def build_host(force=False):
+    """libipic3d_host.so: host C++ helpers (synthetic :U:N universe generator) used by bench.py and tests."""
+    out = os.path.join(HERE, "lib", "libipic3d_host.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not force and os.path.exists(out) and os.path.getmtime(out) > os.path.getmtime(HOST_SRC):
+        return out
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-fvisibility=hidden",
+                           "-ffp-contract=off", "-o", out, HOST_SRC])
+    return out
+
+
 def build(force=False, verbose=False):
     out = os.path.join(HERE, "lib", "libipic3d_b200.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
+    build_host(force)
     if not force and not needs_build(out):
         return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

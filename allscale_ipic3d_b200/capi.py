@@ -215,3 +215,52 @@ class Context:
         a, b, n = C.c_double(0), C.c_double(0), C.c_uint64(0)
         self._ck(self.lib.ipic_profile_get(self.h, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, int(n.value)
+
+
+# -- host-side input generator (host/src/host_capi.cc; not part of the device C ABI) -----------------
+
+_hostlib = None
+
+
+def load_host_library():
+    global _hostlib
+    if _hostlib is None:
+        path = os.path.join(_HERE, "lib", "libipic3d_host.so")
+        if not os.path.exists(path):
+            raise IpicError(-5, "%s is missing: run __graft_entry__.build() first" % path)
+        _hostlib = C.CDLL(path)
+    return _hostlib
+
+
+def uniform_benchmark_props(size=32):
+    """UniverseProperties of the reference's synthetic benchmarks (benchmark.h:13-25, :61-65)."""
+    return Props.make(size, cellWidth=(10.0, 10.0, 10.0), dt=0.15)
+
+
+def uniform_counts(props, num_particles, z_begin=0, z_count=None):
+    """Per-cell populations of the reference's ``:U:N`` universe for the z-planes [z_begin, z_begin+z_count)."""
+    lib = load_host_library()
+    z_count = int(props.size[2]) - z_begin if z_count is None else z_count
+    counts = np.zeros(int(props.size[0] * props.size[1]) * z_count, dtype=np.uint64)
+    rc = lib.ipic_host_uniform_counts(C.byref(props), C.c_uint64(num_particles), C.c_int(z_begin), C.c_int(z_count), _up(counts))
+    if rc:
+        raise IpicError(rc, "ipic_host_uniform_counts: bad arguments")
+    return counts
+
+
+def uniform_particles_into(props, num_particles, aos_ptr, z_begin=0, z_count=None, threads=0):
+    """Fill caller memory (e.g. pinned) with the particles of the ``:U:N`` universe, cell-major AoS."""
+    lib = load_host_library()
+    z_count = int(props.size[2]) - z_begin if z_count is None else z_count
+    rc = lib.ipic_host_uniform_particles(C.byref(props), C.c_uint64(num_particles), C.c_int(z_begin), C.c_int(z_count),
+                                         C.c_void_p(aos_ptr), C.c_int(threads))
+    if rc:
+        raise IpicError(rc, "ipic_host_uniform_particles: bad arguments")
+
+
+def uniform_universe(props, num_particles, z_begin=0, z_count=None, threads=0):
+    counts = uniform_counts(props, num_particles, z_begin, z_count)
+    aos = np.empty((int(counts.sum()), 8), dtype=np.float64)
+    if len(aos):
+        uniform_particles_into(props, num_particles, aos.ctypes.data, z_begin, z_count, threads)
+    return counts, aos
