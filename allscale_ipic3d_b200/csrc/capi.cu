@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -86,14 +87,15 @@ namespace {
 int ownedCells(const ipic_ctx* c) { return c->g.nx * c->g.ny * c->g.lz; }
 
 void freeParticleBuffers(ipic_ctx* c) {
-	for (int b = 0; b < 2; b++) for (int f = 0; f < kFields; f++) { if (c->buf[b].f[f]) cudaFree(c->buf[b].f[f]); c->buf[b].f[f] = nullptr; }
+	for (int b = 0; b < 2; b++) { if (c->buf[b].d) cudaFree(c->buf[b].d); c->buf[b].d = nullptr; }
 	if (c->dTag) cudaFree(c->dTag);
 	c->dTag = nullptr;
 	c->slots = 0;
 }
 
 int allocParticleBuffers(ParticleArrays out[2], unsigned char** tag, int64_t slots) {
-	for (int b = 0; b < 2; b++) for (int f = 0; f < kFields; f++) CK(cudaMalloc(&out[b].f[f], (size_t)std::max<int64_t>(slots, 1) * sizeof(double)));
+	// slots is a multiple of 32: whole AoSoA-32 blocks of 2 KiB
+	for (int b = 0; b < 2; b++) CK(cudaMalloc(&out[b].d, (size_t)std::max<int64_t>(slots, 32) * kFields * sizeof(double)));
 	CK(cudaMalloc(tag, (size_t)std::max<int64_t>(slots, 1)));
 	return IPIC_OK;
 }
@@ -153,6 +155,7 @@ void fillGeometry(ipic_ctx* c) {
 	for (int a = 0; a < 3; a++) {
 		g.w[a] = p.cellWidth[a];
 		g.hw[a] = p.cellWidth[a] / 2.0;
+		g.iw[a] = 1.0 / p.cellWidth[a];
 		g.origin[a] = p.origin[a];
 		g.objectCenter[a] = p.objectCenter[a];
 	}
@@ -168,7 +171,8 @@ void fillGeometry(ipic_ctx* c) {
 int pickItems(const ipic_ctx* c, int64_t total) {
 	const int64_t cells = std::max(1, ownedCells(c));
 	const int64_t avg = total / cells;
-	return avg >= 640 ? 4 : (avg >= 192 ? 2 : 1);
+	if (const char* e = std::getenv("IPIC_ITEMS")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4) return v; }   // tuning knob
+	return avg >= 160 ? 2 : 1;                // particles per thread per tile (tile = items x 128)
 }
 
 cudaEvent_t nextEvent(ipic_ctx* c) {

@@ -16,8 +16,9 @@
 
 namespace ipic {
 
-constexpr int kBlock = 256;
+constexpr int kBlock = 128;                 // threads per CTA of the mover (one CTA per cell)
 constexpr int kWarps = kBlock / 32;
+constexpr int kRedStride = kWarps * 33;     // padded row of the deposit reduction buffer (doubles)
 
 // ---- TMA (bulk async copy) helpers: global -> shared, completion on an mbarrier ------------------
 
@@ -51,9 +52,15 @@ __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p);
 __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
 
 // ---- fused mover + classify (+ deposit) ----------------------------------------------------------
+//
+// One CTA of 128 threads per cell; a tile is ITEMS x 128 consecutive particles of the cell.  Per tile:
+// coalesced loads of the 8 fields (AoSoA-32: one address + immediate offsets), push, classify, one
+// ballot-based stable compaction (1 __syncthreads per tile), coalesced streaming stores.  Several CTAs
+// are resident per SM (launch bounds) so that the load phase of one cell overlaps the arithmetic and the
+// stores of others.
 
 template<int ITEMS, bool INTERP, bool DEPOSIT, bool MIGRATE, bool PUSH>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, DEPOSIT ? 4 : 5)
 k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, const int64_t* __restrict__ cellStart,
        const int* __restrict__ countIn, int* __restrict__ countOut, int* __restrict__ nLeave,
        unsigned char* __restrict__ tag, const double* __restrict__ fieldEB, double* __restrict__ cellJ,
@@ -67,16 +74,16 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	const int cx = xy / g.ny, cy = xy - cx * g.ny, cz = g.z0 + zl;
 	const int cell = xy * g.lzs + zl + g.ghost;
 
-	__shared__ int sStay[ITEMS * kWarps];
-	__shared__ int sLeave[ITEMS * kWarps];
-	__shared__ int sTotal[2];
-	__shared__ alignas(16) double sCorner[48];
+	__shared__ int sCnt[2][ITEMS * kWarps];                      // per (item, warp): stayers | leavers << 16
+	__shared__ alignas(16) double sCorner[INTERP ? 48 : 2];
 	__shared__ uint64_t sBar;
-	__shared__ double sRed[DEPOSIT ? kWarps * 24 : 1];
+	__shared__ double sRed[DEPOSIT ? 24 * kRedStride : 1];
 
 	const int n = countIn[cell];
 	const int64_t base = cellStart[cell];
 	const int cap = (int)(cellStart[cell + 1] - base);
+	const double* __restrict__ src = in.d + (base << 3);         // base is a multiple of 32 slots
+	double* __restrict__ dst = out.d + (base << 3);
 
 	// geometry of this cell (reference universe_properties.h:125-142)
 	double org[3], ctr[3];
@@ -109,18 +116,19 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 		for (int a = 0; a < 24; a++) acc[a] = 0.0;
 	}
 
-	int kept = 0, left = 0;
+	int kept = 0, left = 0, par = 0;
+	const unsigned lt = (1u << lane) - 1u;
 	for (int c0 = 0; c0 < n; c0 += kBlock * ITEMS) {
 		double px[ITEMS], py[ITEMS], pz[ITEMS], vx[ITEMS], vy[ITEMS], vz[ITEMS], pq[ITEMS], pm[ITEMS];
 		unsigned code[ITEMS];
 		#pragma unroll
 		for (int k = 0; k < ITEMS; k++) {
-			const int idx = c0 + k * kBlock + tid;
-			if (idx < n) {
-				const int64_t s = base + idx;
-				px[k] = ld_stream(in.f[0] + s); py[k] = ld_stream(in.f[1] + s); pz[k] = ld_stream(in.f[2] + s);
-				vx[k] = ld_stream(in.f[3] + s); vy[k] = ld_stream(in.f[4] + s); vz[k] = ld_stream(in.f[5] + s);
-				pq[k] = ld_stream(in.f[6] + s); pm[k] = ld_stream(in.f[7] + s);
+			const int t0 = c0 + k * kBlock;                          // first particle of this warp-interleaved sub-tile
+			if (t0 + tid < n) {
+				const double* p = src + ((int64_t)((t0 >> 5) + warp) << 8) + lane;
+				px[k] = ld_stream(p); py[k] = ld_stream(p + 32); pz[k] = ld_stream(p + 64);
+				vx[k] = ld_stream(p + 96); vy[k] = ld_stream(p + 128); vz[k] = ld_stream(p + 160);
+				pq[k] = ld_stream(p + 192); pm[k] = ld_stream(p + 224);
 			}
 		}
 		#pragma unroll
@@ -128,29 +136,29 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 			const int idx = c0 + k * kBlock + tid;
 			code[k] = kTagNone;
 			if (idx < n) {
-				if (DEPOSIT || (INTERP && PUSH)) {
-					// fractional position in the cell (reference cell.h:810, :933)
+				if (DEPOSIT) {
+					// projectToDensityField weights (reference cell.h:810-816); corner (a,b,c) of this cell is the
+					// node the reference reaches with (i,j,k) = (-a,-b,-c).  The per-cell sums are accumulated in
+					// a different order than the reference's sequential loop anyway, so this part uses a
+					// reciprocal multiply and FMAs (J is compared at 1e-12, not bit for bit).
+					const double rx = (px[k] - org[0]) * g.iw[0], ry = (py[k] - org[1]) * g.iw[1], rz = (pz[k] - org[2]) * g.iw[2];
+					const double ox = 1.0 - rx, oy = 1.0 - ry, oz = 1.0 - rz;
+					const double jx = pq[k] * vx[k], jy = pq[k] * vy[k], jz = pq[k] * vz[k];
+					const double wxy[4] = { ox * oy, ox * ry, rx * oy, rx * ry };
+					#pragma unroll
+					for (int ab = 0; ab < 4; ab++) {
+						const double f0 = wxy[ab] * oz, f1 = wxy[ab] * rz;
+						const int o = ab * 6;
+						acc[o] = __fma_rn(jx, f0, acc[o]); acc[o + 1] = __fma_rn(jy, f0, acc[o + 1]); acc[o + 2] = __fma_rn(jz, f0, acc[o + 2]);
+						acc[o + 3] = __fma_rn(jx, f1, acc[o + 3]); acc[o + 4] = __fma_rn(jy, f1, acc[o + 4]); acc[o + 5] = __fma_rn(jz, f1, acc[o + 5]);
+					}
+				}
+				if (INTERP && PUSH) {
+					// fractional position in the cell (reference cell.h:933), kept as a true division: bit-exact
 					const double rx = (px[k] - org[0]) / g.w[0], ry = (py[k] - org[1]) / g.w[1], rz = (pz[k] - org[2]) / g.w[2];
-					if (DEPOSIT) {
-						// projectToDensityField weights (reference cell.h:815-816); corner (a,b,c) of this cell
-						// is the node the reference reaches with (i,j,k) = (-a,-b,-c)
-						const double jx = pq[k] * vx[k], jy = pq[k] * vy[k], jz = pq[k] * vz[k];
-						#pragma unroll
-						for (int a = 0; a < 2; a++)
-							#pragma unroll
-							for (int b = 0; b < 2; b++)
-								#pragma unroll
-								for (int c = 0; c < 2; c++) {
-									const double fac = (a == 0 ? (1 - rx) : rx) * (b == 0 ? (1 - ry) : ry) * (c == 0 ? (1 - rz) : rz);
-									const int o = ((a * 2 + b) * 2 + c) * 3;
-									acc[o] += jx * fac; acc[o + 1] += jy * fac; acc[o + 2] += jz * fac;
-								}
-					}
-					if (INTERP && PUSH) {
-						const Vec3 E = trilinear(sCorner, 6, rx, ry, rz, g.vol);
-						const Vec3 B = trilinear(sCorner + 3, 6, rx, ry, rz, g.vol);
-						push_with_fields(g, px[k], py[k], pz[k], vx[k], vy[k], vz[k], pm[k], E, B);
-					}
+					const Vec3 E = trilinear(sCorner, 6, rx, ry, rz, g.vol);
+					const Vec3 B = trilinear(sCorner + 3, 6, rx, ry, rz, g.vol);
+					push_with_fields(g, px[k], py[k], pz[k], vx[k], vy[k], vz[k], pm[k], E, B);
 				}
 				if (!INTERP && PUSH) {
 					Vec3 E, B;
@@ -164,77 +172,90 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 		if (!PUSH) continue;     // deposit-only pass: nothing is written back
 
 		// stable compaction: order index of an element is k*kBlock + tid
-		unsigned preStay[ITEMS], preLeave[ITEMS];
+		unsigned bs[ITEMS], bl[ITEMS];
 		#pragma unroll
 		for (int k = 0; k < ITEMS; k++) {
-			const bool st = code[k] == 13u, lv = code[k] < 27u && code[k] != 13u;
-			const unsigned bs = __ballot_sync(0xffffffffu, st), bl = __ballot_sync(0xffffffffu, lv);
-			const unsigned lt = (1u << lane) - 1u;
-			preStay[k] = __popc(bs & lt); preLeave[k] = __popc(bl & lt);
-			if (lane == 0) { sStay[k * kWarps + warp] = __popc(bs); sLeave[k * kWarps + warp] = __popc(bl); }
+			bs[k] = __ballot_sync(0xffffffffu, code[k] == 13u);
+			bl[k] = __ballot_sync(0xffffffffu, code[k] < 27u && code[k] != 13u);
+			if (lane == 0) sCnt[par][k * kWarps + warp] = __popc(bs[k]) | (__popc(bl[k]) << 16);
 		}
 		__syncthreads();
-		if (warp == 0) {
-			int a = (lane < ITEMS * kWarps) ? sStay[lane] : 0, b = (lane < ITEMS * kWarps) ? sLeave[lane] : 0;
-			int ia = a, ib = b;
+		int run = 0, mine[ITEMS];
+		#pragma unroll
+		for (int k = 0; k < ITEMS; k++)
 			#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) {
-				const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
-				if (lane >= o) { ia += ta; ib += tb; }
+			for (int w = 0; w < kWarps; w++) {
+				if (w == warp) mine[k] = run;
+				run += sCnt[par][k * kWarps + w];
 			}
-			if (lane < ITEMS * kWarps) { sStay[lane] = ia - a; sLeave[lane] = ib - b; }
-			if (lane == 31) { sTotal[0] = ia; sTotal[1] = ib; }
-		}
-		__syncthreads();
 		#pragma unroll
 		for (int k = 0; k < ITEMS; k++) {
 			const bool st = code[k] == 13u, lv = code[k] < 27u && code[k] != 13u;
 			if (st || lv) {
-				int64_t d;
-				if (st) d = base + kept + sStay[k * kWarps + warp] + (int)preStay[k];
+				int d;
+				if (st) d = kept + (mine[k] & 0xffff) + __popc(bs[k] & lt);
 				else {
-					d = base + cap - 1 - (left + sLeave[k * kWarps + warp] + (int)preLeave[k]);
-					tag[d] = (unsigned char)code[k];
+					d = cap - 1 - (left + (mine[k] >> 16) + __popc(bl[k] & lt));
+					tag[base + d] = (unsigned char)code[k];
 				}
-				st_stream(out.f[0] + d, px[k]); st_stream(out.f[1] + d, py[k]); st_stream(out.f[2] + d, pz[k]);
-				st_stream(out.f[3] + d, vx[k]); st_stream(out.f[4] + d, vy[k]); st_stream(out.f[5] + d, vz[k]);
-				st_stream(out.f[6] + d, pq[k]); st_stream(out.f[7] + d, pm[k]);
+				double* q = dst + ((int64_t)(d >> 5) << 8) + (d & 31);
+				st_stream(q, px[k]); st_stream(q + 32, py[k]); st_stream(q + 64, pz[k]);
+				st_stream(q + 96, vx[k]); st_stream(q + 128, vy[k]); st_stream(q + 160, vz[k]);
+				st_stream(q + 192, pq[k]); st_stream(q + 224, pm[k]);
 			}
 		}
-		kept += sTotal[0]; left += sTotal[1];
-		if (c0 + kBlock * ITEMS < n) __syncthreads();
+		kept += run & 0xffff; left += run >> 16;
+		par ^= 1;
 	}
 	if (PUSH && tid == 0) { countOut[cell] = kept; nLeave[cell] = left; }
 
 	if (DEPOSIT) {
-		// deterministic block reduction of the 8x3 corner sums: lanes (xor tree), then warps in order
+		// deterministic block reduction of the 8x3 corner sums through shared memory:
+		// 96 threads each add 32 partials of one (row, warp) segment in fixed order, then 4 segments per row
 		#pragma unroll
-		for (int a = 0; a < 24; a++) {
-			double v = acc[a];
-			#pragma unroll
-			for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-			if (lane == 0) sRed[warp * 24 + a] = v;
-		}
+		for (int a = 0; a < 24; a++) sRed[a * kRedStride + warp * 33 + lane] = acc[a];
 		__syncthreads();
-		if (tid < 24) {
-			double v = sRed[tid];
+		if (tid < 96) {
+			const int row = tid >> 2, seg = tid & 3;
+			const double* r = sRed + row * kRedStride + seg * 33;
+			double v = r[0];
 			#pragma unroll
-			for (int w = 1; w < kWarps; w++) v += sRed[w * 24 + tid];
-			cellJ[(((int64_t)cx * g.ny + cy) * g.nz + cz) * 24 + tid] = v;      // indexed by GLOBAL cell id
+			for (int i = 1; i < 32; i++) v += r[i];
+			v += __shfl_xor_sync(0xffffffffu, v, 1);
+			v += __shfl_xor_sync(0xffffffffu, v, 2);
+			if (seg == 0) cellJ[(((int64_t)cx * g.ny + cy) * g.nz + cz) * 24 + row] = v;      // indexed by GLOBAL cell id
 		}
 	}
 }
 
 // ---- import: append the 26 incoming outboxes in canonical order (reference cell.h:1195-1310) ------
+//
+// One warp per target cell.  Lane d looks at the neighbour of direction d (lexicographic (0,0,0)..(2,2,2),
+// 13 = self skipped): source cell = target + (a-1,b-1,c-1) with periodic address (transfer_buffer.h,
+// cell.h:1012-1048); the entries of that neighbour's outbox tagged (2-a,2-b,2-c) are ours.  When no
+// neighbour has more than 32 leavers (the common case) all 26 tag rows are fetched at once, the hits are
+// turned into 26 ballots, and every arrival is copied by its own lane: three dependent memory round
+// trips per cell instead of 2 x 26.
 
-__global__ void __launch_bounds__(kBlock)
+constexpr int kImportBlock = 256;
+constexpr int kImportWarps = kImportBlock / 32;
+
+__device__ __forceinline__ void copy_particle(const double* __restrict__ s, double* __restrict__ t) {
+	double v[kFields];
+	#pragma unroll
+	for (int f = 0; f < kFields; f++) v[f] = s[f * kFieldStride];
+	#pragma unroll
+	for (int f = 0; f < kFields; f++) t[f * kFieldStride] = v[f];
+}
+
+__global__ void __launch_bounds__(kImportBlock)
 k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__ srcStart, const int* __restrict__ srcLeave,
          const unsigned char* __restrict__ tag, const ParticleArrays dst, const int64_t* __restrict__ dstStart,
          const int* __restrict__ stay, int* __restrict__ dstCount, int reserveOwnOutbox, int* __restrict__ stopFlag, int stepIndex, int zBegin, int zCount) {
 
 	if (*(volatile int*)stopFlag) return;
 	const int lane = threadIdx.x & 31;
-	const int task = blockIdx.x * kWarps + (threadIdx.x >> 5);
+	const int task = blockIdx.x * kImportWarps + (threadIdx.x >> 5);
 	if (task >= g.nx * g.ny * zCount) return;
 	const int xy = task / zCount;
 	const int zl = zBegin + (task - xy * zCount);
@@ -246,31 +267,77 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 	const int room = dcap - (reserveOwnOutbox ? srcLeave[cell] : 0);
 	int w = stay[cell];
 
-	for (int d = 0; d < 27; d++) {
-		if (d == 13) continue;
-		const int a = d / 9, b = (d / 3) % 3, c = d % 3;
-		// source cell = target + (a-1,b-1,c-1) with periodic address (transfer_buffer.h, cell.h:1012-1048)
+	// lane d: its neighbour's outbox
+	int myLeave = 0;
+	int64_t mySend = 0;
+	if (lane < 27 && lane != 13) {
+		const int a = lane / 9, b = (lane / 3) % 3, c = lane % 3;
 		const int sx = (cx + a - 1 + g.nx) % g.nx, sy = (cy + b - 1 + g.ny) % g.ny;
 		int szl = zl + c - 1;                         // local z; ghost planes hold the neighbours' rows
 		if (!g.ghost) szl = (szl + g.lz) % g.lz;
 		const int scell = (sx * g.ny + sy) * g.lzs + szl + g.ghost;
-		const int nl = srcLeave[scell];
-		if (nl == 0) continue;
-		const unsigned want = (unsigned)((2 - a) * 9 + (2 - b) * 3 + (2 - c));
-		const int64_t send = srcStart[scell + 1] - 1;     // outbox entry j lives at send - j
-		for (int j0 = 0; j0 < nl; j0 += 32) {
-			const int j = j0 + lane;
-			const bool hit = j < nl && tag[send - j] == want;
-			const unsigned m = __ballot_sync(0xffffffffu, hit);
-			if (hit) {
-				const int o = w + __popc(m & ((1u << lane) - 1u));
-				if (o < room) {
-					const int64_t s = send - j, t = dbase + o;
-					#pragma unroll
-					for (int f = 0; f < kFields; f++) dst.f[f][t] = src.f[f][s];
-				}
+		myLeave = srcLeave[scell];
+		mySend = srcStart[scell + 1] - 1;             // outbox entry j lives at slot mySend - j
+	}
+	const int maxLeave = __reduce_max_sync(0xffffffffu, myLeave);
+	if (maxLeave == 0) {
+		if (lane == 0) dstCount[cell] = w;
+		return;
+	}
+
+	if (maxLeave <= 32) {
+		unsigned mask[27];
+		{
+			unsigned char t[27];
+			#pragma unroll
+			for (int d = 0; d < 27; d++) {
+				if (d == 13) continue;
+				const int nl = __shfl_sync(0xffffffffu, myLeave, d);
+				const int64_t send = __shfl_sync(0xffffffffu, mySend, d);
+				t[d] = lane < nl ? tag[send - lane] : kTagNone;
 			}
-			w += __popc(m);
+			#pragma unroll
+			for (int d = 0; d < 27; d++) {
+				if (d == 13) { mask[d] = 0; continue; }
+				const unsigned want = (unsigned)((2 - d / 9) * 9 + (2 - (d / 3) % 3) * 3 + (2 - d % 3));
+				mask[d] = __ballot_sync(0xffffffffu, t[d] == want);
+			}
+		}
+		int total = 0;
+		#pragma unroll
+		for (int d = 0; d < 27; d++) total += __popc(mask[d]);
+		for (int i0 = 0; i0 < total; i0 += 32) {
+			const int i = i0 + lane;
+			int pre = 0, dsel = 0, jsel = 0;
+			#pragma unroll
+			for (int d = 0; d < 27; d++) {
+				const int cnt = __popc(mask[d]);
+				if (i >= pre && i < pre + cnt) { dsel = d; jsel = (int)__fns(mask[d], 0, i - pre + 1); }
+				pre += cnt;
+			}
+			const int64_t send = __shfl_sync(0xffffffffu, mySend, dsel);
+			if (i < total && w + i < room)
+				copy_particle(src.d + slot_index(send - jsel), dst.d + slot_index(dbase + w + i));
+		}
+		w += total;
+	} else {
+		// general path: direction after direction, 32 outbox entries per round
+		for (int d = 0; d < 27; d++) {
+			if (d == 13) continue;
+			const int nl = __shfl_sync(0xffffffffu, myLeave, d);
+			if (nl == 0) continue;
+			const int64_t send = __shfl_sync(0xffffffffu, mySend, d);
+			const unsigned want = (unsigned)((2 - d / 9) * 9 + (2 - (d / 3) % 3) * 3 + (2 - d % 3));
+			for (int j0 = 0; j0 < nl; j0 += 32) {
+				const int j = j0 + lane;
+				const bool hit = j < nl && tag[send - j] == want;
+				const unsigned m = __ballot_sync(0xffffffffu, hit);
+				if (hit) {
+					const int o = w + __popc(m & ((1u << lane) - 1u));
+					if (o < room) copy_particle(src.d + slot_index(send - j), dst.d + slot_index(dbase + o));
+				}
+				w += __popc(m);
+			}
 		}
 	}
 	if (lane == 0) {
@@ -321,7 +388,8 @@ __global__ void k_count_misplaced(const Geometry g, const ParticleArrays p, cons
 	const int64_t base = cellStart[cell];
 	unsigned long long local = 0;
 	for (int i = threadIdx.x; i < count[cell]; i += blockDim.x) {
-		const bool ok = fabs(p.f[0][base + i] - c0) <= g.hw[0] && fabs(p.f[1][base + i] - c1) <= g.hw[1] && fabs(p.f[2][base + i] - c2) <= g.hw[2];
+		const double* q = p.d + slot_index(base + i);
+		const bool ok = fabs(q[0] - c0) <= g.hw[0] && fabs(q[kFieldStride] - c1) <= g.hw[1] && fabs(q[2 * kFieldStride] - c2) <= g.hw[2];
 		if (!ok) local++;
 	}
 	if (local) atomicAdd(bad, local);
@@ -337,7 +405,7 @@ __global__ void k_scatter_aos(const Geometry g, const double* __restrict__ aos, 
 	const int zl = oc % g.lz, xy = oc / g.lz;
 	const int cell = xy * g.lzs + zl + g.ghost;
 	const int64_t a0 = aosStart[oc], n = aosStart[oc + 1] - a0, base = cellStart[cell];
-	for (int64_t e = threadIdx.x; e < n * 8; e += blockDim.x) p.f[e & 7][base + (e >> 3)] = aos[a0 * 8 + e];
+	for (int64_t e = threadIdx.x; e < n * 8; e += blockDim.x) p.d[slot_index(base + (e >> 3)) + (e & 7) * kFieldStride] = aos[a0 * 8 + e];
 }
 
 __global__ void k_gather_aos(const Geometry g, double* __restrict__ aos, const int64_t* __restrict__ aosStart,
@@ -346,7 +414,7 @@ __global__ void k_gather_aos(const Geometry g, double* __restrict__ aos, const i
 	const int zl = oc % g.lz, xy = oc / g.lz;
 	const int cell = xy * g.lzs + zl + g.ghost;
 	const int64_t a0 = aosStart[oc], n = aosStart[oc + 1] - a0, base = cellStart[cell];
-	for (int64_t e = threadIdx.x; e < n * 8; e += blockDim.x) aos[a0 * 8 + e] = p.f[e & 7][base + (e >> 3)];
+	for (int64_t e = threadIdx.x; e < n * 8; e += blockDim.x) aos[a0 * 8 + e] = p.d[slot_index(base + (e >> 3)) + (e & 7) * kFieldStride];
 }
 
 // copy the live head of every owned cell from one layout to another (relayout)
@@ -357,8 +425,11 @@ __global__ void k_copy_heads(const Geometry g, const ParticleArrays src, const i
 	const int cell = xy * g.lzs + zl + g.ghost;
 	const int64_t s0 = srcStart[cell], d0 = dstStart[cell];
 	const int n = count[cell];
-	for (int f = 0; f < kFields; f++)
-		for (int i = threadIdx.x; i < n; i += blockDim.x) dst.f[f][d0 + i] = src.f[f][s0 + i];
+	// both segment starts are multiples of 32 slots: whole AoSoA blocks line up, copy them double by double
+	const int64_t doubles = ((int64_t)(n + 31) >> 5) << 8;
+	const double* s = src.d + (s0 << 3);
+	double* d = dst.d + (d0 << 3);
+	for (int64_t i = threadIdx.x; i < doubles; i += blockDim.x) d[i] = s[i];
 }
 
 // ---- launchers -----------------------------------------------------------------------------------
@@ -389,7 +460,7 @@ void launch_move(const MoveArgs& a, cudaStream_t st) {
 void launch_import(const ImportArgs& a, cudaStream_t st) {
 	const int tasks = a.g.nx * a.g.ny * a.zCount;
 	if (tasks == 0) return;
-	k_import<<<(tasks + kWarps - 1) / kWarps, kBlock, 0, st>>>(a.g, a.src, a.srcStart, a.srcLeave, a.tag, a.dst, a.dstStart, a.stay, a.dstCount,
+	k_import<<<(tasks + kImportWarps - 1) / kImportWarps, kImportBlock, 0, st>>>(a.g, a.src, a.srcStart, a.srcLeave, a.tag, a.dst, a.dstStart, a.stay, a.dstCount,
 	                                                         a.reserveOwnOutbox, a.stopFlag, a.stepIndex, a.zBegin, a.zCount);
 	k_commit_flag<<<1, 1, 0, st>>>(a.stopFlag);
 }
