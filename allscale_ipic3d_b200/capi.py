@@ -19,7 +19,7 @@ API_SYMBOLS = [
     "ipic_last_error", "ipic_version", "ipic_device_count", "ipic_create", "ipic_create_slab", "ipic_destroy",
     "ipic_set_headroom", "ipic_comm_unique_id", "ipic_comm_init", "ipic_upload_cells", "ipic_download_cells",
     "ipic_cell_counts", "ipic_total_particles", "ipic_upload_fields", "ipic_download_fields", "ipic_step",
-    "ipic_step_async", "ipic_sync", "ipic_count_misplaced", "ipic_profile_reset", "ipic_profile_get",
+    "ipic_step_async", "ipic_sync", "ipic_count_misplaced", "ipic_profile_reset", "ipic_profile_get", "ipic_selftest",
 ]
 
 
@@ -215,6 +215,16 @@ class Context:
         a, b, n = C.c_double(0), C.c_double(0), C.c_uint64(0)
         self._ck(self.lib.ipic_profile_get(self.h, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, int(n.value)
+
+
+def selftest(n=1 << 22, seed=1, device=0):
+    """Device self-test of the FP64 helpers (see ipic_selftest); returns the number of mismatches (must be 0)."""
+    lib = load_library()
+    bad = C.c_uint64(0)
+    rc = lib.ipic_selftest(C.c_int(device), C.c_uint64(n), C.c_uint64(seed), C.byref(bad))
+    if rc:
+        raise IpicError(rc, lib.ipic_last_error().decode())
+    return int(bad.value)
 
 
 # -- host-side input generator (host/src/host_capi.cc; not part of the device C ABI) -----------------

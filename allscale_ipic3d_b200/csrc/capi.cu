@@ -56,7 +56,7 @@ struct ipic_ctx {
 	unsigned char* dTag = nullptr;                 // direction tag per slot (outbox entries only)
 	int* dStop = nullptr;                          // [0] stop, [1] first failing step, [2] overflow seen
 	bool haveCells = false;
-	int items = 2;                                 // particles per thread in the mover tile (from the mean population)
+	int64_t meanPopulation = 0;                    // particles per owned cell at upload (drives the mover's tile shape)
 	double slack = 0.25;                           // head-room per cell as a fraction of its population
 	int64_t minPad = 64;                           // ... and in absolute slots
 
@@ -168,11 +168,17 @@ void fillGeometry(ipic_ctx* c) {
 	g.vol = p.cellWidth[0] * p.cellWidth[1] * p.cellWidth[2];
 }
 
-int pickItems(const ipic_ctx* c, int64_t total) {
-	const int64_t cells = std::max(1, ownedCells(c));
-	const int64_t avg = total / cells;
-	if (const char* e = std::getenv("IPIC_ITEMS")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4) return v; }   // tuning knob
-	return avg >= 160 ? 2 : 1;                // particles per thread per tile (tile = items x 128)
+// Tile shape of the mover, from the mean cell population (measured on B200, profiles/README.md): one
+// particle per thread keeps the register count at 96 (5 CTAs per SM) and is fastest for the plain mover;
+// with the fused deposit (24 accumulators per thread) two particles per thread amortise the per-cell
+// reduction better.  Stages: enough tiles to have an average cell completely in flight.
+void pickTileShape(const ipic_ctx* c, bool deposit, int& items, int& stages) {
+	const int64_t avg = c->meanPopulation;
+	items = (deposit && avg >= 160) ? 2 : 1;
+	if (const char* e = std::getenv("IPIC_ITEMS")) { const int v = std::atoi(e); if (v == 1 || v == 2) items = v; }     // tuning knob
+	const int64_t tile = (int64_t)items * 128;
+	stages = (int)std::max<int64_t>(2, std::min<int64_t>((avg + avg / 8 + tile - 1) / tile, items == 2 ? 3 : 4));
+	if (const char* e = std::getenv("IPIC_STAGES")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) stages = v; }   // tuning knob
 }
 
 cudaEvent_t nextEvent(ipic_ctx* c) {
@@ -349,7 +355,7 @@ int ipic_upload_cells(ipic_ctx* c, const uint64_t* counts, const double* aos) {
 	}
 	CK(cudaStreamSynchronize(c->stream));     // host vectors above go out of scope
 	c->haveCells = true;
-	c->items = pickItems(c, total);
+	c->meanPopulation = total / std::max(1, nOwned);
 	return IPIC_OK;
 }
 
@@ -430,7 +436,6 @@ int ipic_download_fields(ipic_ctx* c, double* field, double* bc, double* J) {
 
 // One iteration of the time loop, enqueued on the context's stream.
 static int enqueueStep(ipic_ctx* c, uint32_t flags, int stepIndex) {
-	const int items = c->items;
 	const bool interp = flags & IPIC_MOVER_INTERPOLATED;
 	const bool project = flags & IPIC_PROJECT_CURRENT;
 	const bool solve = flags & (IPIC_SOLVER_FORWARD | IPIC_SOLVER_LEAPFROG);
@@ -441,7 +446,7 @@ static int enqueueStep(ipic_ctx* c, uint32_t flags, int stepIndex) {
 	ma.g = c->g; ma.in = c->buf[in]; ma.out = c->buf[out]; ma.cellStart = c->dCellStart;
 	ma.countIn = c->dCount; ma.countOut = c->dStay; ma.nLeave = c->dLeave; ma.tag = c->dTag;
 	ma.fieldEB = c->dEB; ma.cellJ = c->dCellJ; ma.stopFlag = c->dStop;
-	ma.zBegin = 0; ma.zCount = c->g.lz; ma.itemsPerThread = items;
+	ma.zBegin = 0; ma.zCount = c->g.lz;
 	ma.interpolate = interp; ma.migrate = migrate; ma.push = true;
 
 	auto fieldPhase = [&]() {
@@ -456,6 +461,7 @@ static int enqueueStep(ipic_ctx* c, uint32_t flags, int stepIndex) {
 	const bool fuseDeposit = project && !interp;
 	if (project && interp) {
 		MoveArgs da = ma; da.push = false; da.deposit = true; da.interpolate = false;
+		pickTileShape(c, true, da.itemsPerThread, da.stages);
 		launch_move(da, c->stream);
 		launch_gather_current(c->g, c->dCellJ, c->dJ, c->dStop, c->stream);
 		c->launches += 2;
@@ -465,6 +471,7 @@ static int enqueueStep(ipic_ctx* c, uint32_t flags, int stepIndex) {
 	cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
 	if (c->profiling) { e0 = nextEvent(c); e1 = nextEvent(c); e2 = nextEvent(c); cudaEventRecord(e0, c->stream); }
 	ma.deposit = fuseDeposit;
+	pickTileShape(c, ma.deposit, ma.itemsPerThread, ma.stages);
 	launch_move(ma, c->stream);
 	c->launches++;
 	if (c->profiling) cudaEventRecord(e1, c->stream);
@@ -580,6 +587,23 @@ int ipic_count_misplaced(ipic_ctx* c, uint64_t* misplaced) {
 	CK(cudaStreamSynchronize(c->stream));
 	cudaFree(d);
 	*misplaced = h;
+	return IPIC_OK;
+}
+
+int ipic_selftest(int device, uint64_t n, uint64_t seed, uint64_t* mismatches) {
+	if (!mismatches) return fail(IPIC_ERR_ARG, "null argument");
+	int ndev = 0;
+	CK(cudaGetDeviceCount(&ndev));
+	if (device < 0 || device >= ndev) return fail(IPIC_ERR_CUDA, "CUDA device %d not available (%d devices)", device, ndev);
+	CK(cudaSetDevice(device));
+	unsigned long long* d = nullptr;
+	CK(cudaMalloc(&d, sizeof(unsigned long long)));
+	CK(cudaMemset(d, 0, sizeof(unsigned long long)));
+	launch_selftest_division(n, seed, d, nullptr);
+	unsigned long long h = 0;
+	CK(cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost));
+	cudaFree(d);
+	*mismatches = h;
 	return IPIC_OK;
 }
 

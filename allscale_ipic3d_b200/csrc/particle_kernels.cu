@@ -14,6 +14,8 @@
 #include "ipic_device.cuh"
 #include "particle_kernels.h"
 
+#include <algorithm>
+
 namespace ipic {
 
 constexpr int kBlock = 128;                 // threads per CTA of the mover (one CTA per cell)
@@ -35,36 +37,44 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+	uint32_t ok;
 	asm volatile(
 		"{\n"
 		".reg .pred p;\n"
-		"WAIT_LOOP:\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-		"@p bra WAIT_DONE;\n"
-		"bra WAIT_LOOP;\n"
-		"WAIT_DONE:\n"
-		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+		"selp.u32 %0, 1, 0, p;\n"
+		"}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	while (!mbar_try_wait(bar, parity)) { }
 }
 
-// streaming (read-once / write-once) accesses: keep L1 clean, let L2 evict first
-__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+// streaming (write-once) stores: let L2 evict first
 __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
 
 // ---- fused mover + classify (+ deposit) ----------------------------------------------------------
 //
-// One CTA of 128 threads per cell; a tile is ITEMS x 128 consecutive particles of the cell.  Per tile:
-// coalesced loads of the 8 fields (AoSoA-32: one address + immediate offsets), push, classify, one
-// ballot-based stable compaction (1 __syncthreads per tile), coalesced streaming stores.  Several CTAs
-// are resident per SM (launch bounds) so that the load phase of one cell overlaps the arithmetic and the
-// stores of others.
+// One CTA of 128 threads per cell; a tile is ITEMS x 128 consecutive particles of the cell = ITEMS x 4
+// AoSoA blocks = one contiguous chunk of HBM.  At CTA start one thread queues TMA bulk copies
+// (cp.async.bulk, completion on an mbarrier per stage) for the first `stages` tiles, i.e. normally for
+// the WHOLE cell, so all of a cell's bytes are in flight before the first particle is pushed; the
+// warps then consume tile after tile out of shared memory: push, classify, one ballot-based stable
+// compaction (one __syncthreads per tile, after which the stage is re-armed for tile t+stages), and
+// coalesced streaming stores straight from registers.  3-4 CTAs are resident per SM.
+
+constexpr int kMaxStages = 8;
 
 template<int ITEMS, bool INTERP, bool DEPOSIT, bool MIGRATE, bool PUSH>
-__global__ void __launch_bounds__(kBlock, DEPOSIT ? 4 : 5)
+__global__ void __launch_bounds__(kBlock, DEPOSIT ? 3 : 4)
 k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, const int64_t* __restrict__ cellStart,
        const int* __restrict__ countIn, int* __restrict__ countOut, int* __restrict__ nLeave,
        unsigned char* __restrict__ tag, const double* __restrict__ fieldEB, double* __restrict__ cellJ,
-       const int* __restrict__ stopFlag, int zBegin, int zCount) {
+       const int* __restrict__ stopFlag, int zBegin, int zCount, int stages) {
+
+	constexpr int TILE = ITEMS * kBlock;
+	constexpr int TILE_DOUBLES = TILE * kFields;
 
 	if (*stopFlag) return;
 
@@ -74,29 +84,38 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	const int cx = xy / g.ny, cy = xy - cx * g.ny, cz = g.z0 + zl;
 	const int cell = xy * g.lzs + zl + g.ghost;
 
+	extern __shared__ __align__(128) double sTile[];             // stages x TILE_DOUBLES (reused by the deposit reduction)
+	__shared__ uint64_t sFull[kMaxStages];
 	__shared__ int sCnt[2][ITEMS * kWarps];                      // per (item, warp): stayers | leavers << 16
-	__shared__ alignas(16) double sCorner[INTERP ? 48 : 2];
+	__shared__ alignas(16) double sCorner[48];
 	__shared__ uint64_t sBar;
-	__shared__ double sRed[DEPOSIT ? 24 * kRedStride : 1];
 
 	const int n = countIn[cell];
 	const int64_t base = cellStart[cell];
 	const int cap = (int)(cellStart[cell + 1] - base);
 	const double* __restrict__ src = in.d + (base << 3);         // base is a multiple of 32 slots
 	double* __restrict__ dst = out.d + (base << 3);
+	const int nTiles = (n + TILE - 1) / TILE;
 
-	// geometry of this cell (reference universe_properties.h:125-142)
-	double org[3], ctr[3];
-	org[0] = g.origin[0] + (double)cx * g.w[0];
-	org[1] = g.origin[1] + (double)cy * g.w[1];
-	org[2] = g.origin[2] + (double)cz * g.w[2];
-	ctr[0] = org[0] + g.hw[0]; ctr[1] = org[1] + g.hw[1]; ctr[2] = org[2] + g.hw[2];
+	if (tid == 0) {
+		for (int s = 0; s < stages; s++) mbar_init(&sFull[s], 1);
+		if (INTERP && PUSH) mbar_init(&sBar, 1);
+	}
+	__syncthreads();
 
-	if (INTERP && PUSH) {
-		// stage the 8 corner (E,B) values of this cell: 4 bulk copies of one z-pair of nodes (96 B) each
-		if (tid == 0) mbar_init(&sBar, 1);
-		__syncthreads();
-		if (tid == 0 && n > 0) {
+	// queue tile t (whole AoSoA blocks; the unused lanes of the last block are never looked at)
+	auto issue = [&](int t, int s) {
+		const int first = t * TILE;
+		const int cnt = min(TILE, n - first);
+		const uint32_t bytes = (uint32_t)((cnt + 31) >> 5) * (32 * kFields * 8);
+		mbar_expect_tx(&sFull[s], bytes);
+		tma_bulk_g2s(sTile + s * TILE_DOUBLES, src + (int64_t)first * kFields, bytes, &sFull[s]);
+	};
+	if (tid == 0) {
+		const int pre = min(stages, nTiles);
+		for (int t = 0; t < pre; t++) issue(t, t);
+		if (INTERP && PUSH && n > 0) {
+			// the 8 corner (E,B) values of this cell: 4 bulk copies of one z-pair of nodes (96 B) each
 			mbar_expect_tx(&sBar, 4 * 96);
 			const int fy = g.ny + 3, fz = g.nz + 3;
 			#pragma unroll
@@ -107,8 +126,16 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 					tma_bulk_g2s(&sCorner[(i * 2 + j) * 12], fieldEB + node * 6, 96, &sBar);
 				}
 		}
-		if (n > 0) mbar_wait(&sBar, 0);
 	}
+
+	// geometry of this cell (reference universe_properties.h:125-142)
+	double org[3], ctr[3];
+	org[0] = g.origin[0] + (double)cx * g.w[0];
+	org[1] = g.origin[1] + (double)cy * g.w[1];
+	org[2] = g.origin[2] + (double)cz * g.w[2];
+	ctr[0] = org[0] + g.hw[0]; ctr[1] = org[1] + g.hw[1]; ctr[2] = org[2] + g.hw[2];
+
+	if (INTERP && PUSH && n > 0) mbar_wait(&sBar, 0);
 
 	double acc[DEPOSIT ? 24 : 1];
 	if (DEPOSIT) {
@@ -117,18 +144,21 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	}
 
 	int kept = 0, left = 0, par = 0;
+	int stage = 0; uint32_t phase = 0;
 	const unsigned lt = (1u << lane) - 1u;
-	for (int c0 = 0; c0 < n; c0 += kBlock * ITEMS) {
+	for (int t = 0; t < nTiles; t++) {
+		const int c0 = t * TILE;
 		double px[ITEMS], py[ITEMS], pz[ITEMS], vx[ITEMS], vy[ITEMS], vz[ITEMS], pq[ITEMS], pm[ITEMS];
 		unsigned code[ITEMS];
+		mbar_wait(&sFull[stage], phase);
+		const double* tile = sTile + stage * TILE_DOUBLES;
 		#pragma unroll
 		for (int k = 0; k < ITEMS; k++) {
-			const int t0 = c0 + k * kBlock;                          // first particle of this warp-interleaved sub-tile
-			if (t0 + tid < n) {
-				const double* p = src + ((int64_t)((t0 >> 5) + warp) << 8) + lane;
-				px[k] = ld_stream(p); py[k] = ld_stream(p + 32); pz[k] = ld_stream(p + 64);
-				vx[k] = ld_stream(p + 96); vy[k] = ld_stream(p + 128); vz[k] = ld_stream(p + 160);
-				pq[k] = ld_stream(p + 192); pm[k] = ld_stream(p + 224);
+			if (c0 + k * kBlock + tid < n) {
+				const double* p = tile + ((k * kWarps + warp) << 8) + lane;
+				px[k] = p[0]; py[k] = p[32]; pz[k] = p[64];
+				vx[k] = p[96]; vy[k] = p[128]; vz[k] = p[160];
+				pq[k] = p[192]; pm[k] = p[224];
 			}
 		}
 		#pragma unroll
@@ -169,17 +199,21 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 			}
 		}
 
-		if (!PUSH) continue;     // deposit-only pass: nothing is written back
-
 		// stable compaction: order index of an element is k*kBlock + tid
 		unsigned bs[ITEMS], bl[ITEMS];
-		#pragma unroll
-		for (int k = 0; k < ITEMS; k++) {
-			bs[k] = __ballot_sync(0xffffffffu, code[k] == 13u);
-			bl[k] = __ballot_sync(0xffffffffu, code[k] < 27u && code[k] != 13u);
-			if (lane == 0) sCnt[par][k * kWarps + warp] = __popc(bs[k]) | (__popc(bl[k]) << 16);
+		if (PUSH) {
+			#pragma unroll
+			for (int k = 0; k < ITEMS; k++) {
+				bs[k] = __ballot_sync(0xffffffffu, code[k] == 13u);
+				bl[k] = __ballot_sync(0xffffffffu, code[k] < 27u && code[k] != 13u);
+				if (lane == 0) sCnt[par][k * kWarps + warp] = __popc(bs[k]) | (__popc(bl[k]) << 16);
+			}
 		}
-		__syncthreads();
+		__syncthreads();                                         // every thread has its tile in registers: stage is free
+		if (tid == 0 && t + stages < nTiles) issue(t + stages, stage);
+		if (++stage == stages) { stage = 0; phase ^= 1; }
+		if (!PUSH) continue;                                     // deposit-only pass: nothing is written back
+
 		int run = 0, mine[ITEMS];
 		#pragma unroll
 		for (int k = 0; k < ITEMS; k++)
@@ -210,8 +244,11 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	if (PUSH && tid == 0) { countOut[cell] = kept; nLeave[cell] = left; }
 
 	if (DEPOSIT) {
-		// deterministic block reduction of the 8x3 corner sums through shared memory:
-		// 96 threads each add 32 partials of one (row, warp) segment in fixed order, then 4 segments per row
+		// deterministic block reduction of the 8x3 corner sums through shared memory (the tile stages are
+		// idle by now): 96 threads each add 32 partials of one (row, warp) segment in fixed order, then the
+		// 4 segments of a row are combined by two shuffles
+		double* sRed = sTile;
+		__syncthreads();
 		#pragma unroll
 		for (int a = 0; a < 24; a++) sRed[a * kRedStride + warp * 33 + lane] = acc[a];
 		__syncthreads();
@@ -432,17 +469,65 @@ __global__ void k_copy_heads(const Geometry g, const ParticleArrays src, const i
 	for (int64_t i = threadIdx.x; i < doubles; i += blockDim.x) d[i] = s[i];
 }
 
+// ---- device self-test of the arithmetic helpers ---------------------------------------------------
+
+// counts inputs for which div3_ge1 differs (bitwise) from IEEE division; inputs are pseudo-random with
+// exponents spread over the range the Boris rotation can produce, and exact zeros mixed in
+__global__ void k_selftest_division(uint64_t n, uint64_t seed, unsigned long long* __restrict__ bad) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint64_t st = seed + i * 0x9E3779B97F4A7C15ull;
+	auto next = [&]() { st ^= st >> 30; st *= 0xBF58476D1CE4E5B9ull; st ^= st >> 27; st *= 0x94D049BB133111EBull; st ^= st >> 31; return st; };
+	auto value = [&]() {
+		const uint64_t r = next();
+		if ((r & 15) == 0) return (r & 16) ? -0.0 : 0.0;
+		const double m = 1.0 + (double)(next() >> 11) * (1.0 / 9007199254740992.0);
+		const int e = (int)((r >> 8) % 121) - 60;
+		return ((r & 32) ? -m : m) * exp2((double)e);
+	};
+	const double tx = value(), ty = value(), tz = value();
+	double t2 = 0.0 + tx * tx; t2 += ty * ty; t2 += tz * tz;
+	const double den = 1.0 + t2;
+	double x = 2.0 * tx, y = 2.0 * ty, z = 2.0 * tz;
+	const double wx = x / den, wy = y / den, wz = z / den;
+	div3_ge1(x, y, z, den);
+	if (__double_as_longlong(x) != __double_as_longlong(wx) || __double_as_longlong(y) != __double_as_longlong(wy) ||
+	    __double_as_longlong(z) != __double_as_longlong(wz)) atomicAdd(bad, 1ull);
+}
+
+void launch_selftest_division(uint64_t n, uint64_t seed, unsigned long long* bad, cudaStream_t st) {
+	k_selftest_division<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, seed, bad);
+}
+
 // ---- launchers -----------------------------------------------------------------------------------
+
+// dynamic shared memory of one CTA: the tile stages, and at least the deposit reduction buffer
+static size_t move_smem_bytes(int items, int stages, bool deposit) {
+	size_t b = (size_t)stages * items * kBlock * kFields * sizeof(double);
+	if (deposit) b = std::max(b, (size_t)24 * kRedStride * sizeof(double));
+	return b;
+}
+
+template<int ITEMS, bool INTERP, bool DEPOSIT, bool MIGRATE, bool PUSH>
+static void launch_move_k(const MoveArgs& a, int grid, cudaStream_t st) {
+	static bool configured = false;                  // opt in to > 48 KiB of dynamic shared memory once per instantiation
+	auto kernel = k_move<ITEMS, INTERP, DEPOSIT, MIGRATE, PUSH>;
+	if (!configured) {
+		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)move_smem_bytes(ITEMS, kMaxStages, DEPOSIT));
+		configured = true;
+	}
+	const int stages = std::max(1, std::min(a.stages, kMaxStages));
+	kernel<<<grid, kBlock, move_smem_bytes(ITEMS, stages, DEPOSIT), st>>>(a.g, a.in, a.out, a.cellStart, a.countIn, a.countOut, a.nLeave, a.tag,
+	                                                                     a.fieldEB, a.cellJ, a.stopFlag, a.zBegin, a.zCount, stages);
+}
 
 template<int ITEMS, bool INTERP, bool DEPOSIT>
 static void launch_move_t(const MoveArgs& a, cudaStream_t st) {
 	const int grid = a.g.nx * a.g.ny * a.zCount;
 	if (grid == 0) return;
-#define IPIC_MOVE_ARGS a.g, a.in, a.out, a.cellStart, a.countIn, a.countOut, a.nLeave, a.tag, a.fieldEB, a.cellJ, a.stopFlag, a.zBegin, a.zCount
-	if (!a.push) { if (DEPOSIT) k_move<ITEMS, false, DEPOSIT, false, false><<<grid, kBlock, 0, st>>>(IPIC_MOVE_ARGS); }
-	else if (a.migrate) k_move<ITEMS, INTERP, DEPOSIT, true, true><<<grid, kBlock, 0, st>>>(IPIC_MOVE_ARGS);
-	else k_move<ITEMS, INTERP, DEPOSIT, false, true><<<grid, kBlock, 0, st>>>(IPIC_MOVE_ARGS);
-#undef IPIC_MOVE_ARGS
+	if (!a.push) { if (DEPOSIT) launch_move_k<ITEMS, false, DEPOSIT, false, false>(a, grid, st); }
+	else if (a.migrate) launch_move_k<ITEMS, INTERP, DEPOSIT, true, true>(a, grid, st);
+	else launch_move_k<ITEMS, INTERP, DEPOSIT, false, true>(a, grid, st);
 }
 
 template<int ITEMS>
@@ -452,8 +537,7 @@ static void launch_move_i(const MoveArgs& a, cudaStream_t st) {
 }
 
 void launch_move(const MoveArgs& a, cudaStream_t st) {
-	if (a.itemsPerThread >= 4) launch_move_i<4>(a, st);
-	else if (a.itemsPerThread >= 2) launch_move_i<2>(a, st);
+	if (a.itemsPerThread >= 2) launch_move_i<2>(a, st);
 	else launch_move_i<1>(a, st);
 }
 

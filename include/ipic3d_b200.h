@@ -113,6 +113,11 @@ IPIC_API int  ipic_sync(ipic_ctx* ctx);
  * particles outside the closed box of their cell. */
 IPIC_API int  ipic_count_misplaced(ipic_ctx* ctx, uint64_t* misplaced);
 
+/* Device self-test of the FP64 helpers that replace library code on the hot path (shared-reciprocal
+ * division of the Boris rotation): number of random inputs (out of n) whose result is not bit-identical
+ * to IEEE division.  Must be 0. */
+IPIC_API int  ipic_selftest(int device, uint64_t n, uint64_t seed, uint64_t* mismatches);
+
 /* Measurement support: device time (ms) of the mover / import kernels accumulated since the last
  * reset, and the number of kernel launches issued. */
 IPIC_API int  ipic_profile_reset(ipic_ctx* ctx);

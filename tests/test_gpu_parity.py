@@ -39,6 +39,13 @@ def assert_particles_close(got, want, tol=TOL):
     assert norm_rel_err(got[:, 3:6], want[:, 3:6]) <= tol
 
 
+def test_division_selftest():
+    """The shared-reciprocal division of the Boris rotation is bit-identical to IEEE division (16M random inputs)."""
+    from allscale_ipic3d_b200 import capi
+    assert capi.selftest(1 << 24, seed=7) == 0
+    assert capi.selftest(1 << 22, seed=12345) == 0
+
+
 def test_small_dipole_golden(golden_dir):
     """4^3 Earth-dipole universe: reflection at all walls, planet absorption, 20 steps vs committed reference output."""
     g = np.load(os.path.join(golden_dir, "small_dipole.npz"))
