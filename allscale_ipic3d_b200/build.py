@@ -32,14 +32,14 @@ def build_host(force=False):
     return out
 
 
-def build(force=False, verbose=False):
-    out = os.path.join(HERE, "lib", "libipic3d_b200.so")
+def build(force=False, verbose=False, defines=(), name="libipic3d_b200.so"):
+    out = os.path.join(HERE, "lib", name)
     os.makedirs(os.path.dirname(out), exist_ok=True)
     build_host(force)
     if not force and not needs_build(out):
         return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    cmd = [nvcc] + FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     subprocess.check_call(cmd)
     return out
 

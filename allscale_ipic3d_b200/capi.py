@@ -66,7 +66,8 @@ class Props(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "libipic3d_b200.so")
+    # IPIC_LIB: tuning builds of the same sources with other compile-time knobs (scripts/variants.py)
+    return os.environ.get("IPIC_LIB") or os.path.join(_HERE, "lib", "libipic3d_b200.so")
 
 
 _lib = None

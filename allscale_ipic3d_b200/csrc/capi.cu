@@ -168,16 +168,16 @@ void fillGeometry(ipic_ctx* c) {
 	g.vol = p.cellWidth[0] * p.cellWidth[1] * p.cellWidth[2];
 }
 
-// Tile shape of the mover, from the mean cell population (measured on B200, profiles/README.md): one
-// particle per thread keeps the register count at 96 (5 CTAs per SM) and is fastest for the plain mover;
-// with the fused deposit (24 accumulators per thread) two particles per thread amortise the per-cell
-// reduction better.  Stages: enough tiles to have an average cell completely in flight.
+// Tile shape of the mover (measured on B200, profiles/README.md): the kernel is bound by how many warps
+// are resident, so one particle per thread (72 / 96 registers, 7 / 5 CTAs per SM) wins over two, and few
+// stages win over many (shared memory caps the CTAs per SM): 2 stages = 16 KiB for the plain mover; with
+// the fused deposit a batch of 4 stages amortises the per-batch block reduction of the 24 corner sums.
 void pickTileShape(const ipic_ctx* c, bool deposit, int& items, int& stages) {
 	const int64_t avg = c->meanPopulation;
-	items = (deposit && avg >= 160) ? 2 : 1;
+	items = 1;
 	if (const char* e = std::getenv("IPIC_ITEMS")) { const int v = std::atoi(e); if (v == 1 || v == 2) items = v; }     // tuning knob
 	const int64_t tile = (int64_t)items * 128;
-	stages = (int)std::max<int64_t>(2, std::min<int64_t>((avg + avg / 8 + tile - 1) / tile, items == 2 ? 3 : 4));
+	stages = (int)std::max<int64_t>(1, std::min<int64_t>((avg + avg / 8 + tile - 1) / tile, deposit ? 4 : 2));
 	if (const char* e = std::getenv("IPIC_STAGES")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) stages = v; }   // tuning knob
 }
 

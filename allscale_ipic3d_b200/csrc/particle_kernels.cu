@@ -20,7 +20,7 @@ namespace ipic {
 
 constexpr int kBlock = 128;                 // threads per CTA of the mover (one CTA per cell)
 constexpr int kWarps = kBlock / 32;
-constexpr int kRedStride = kWarps * 33;     // padded row of the deposit reduction buffer (doubles)
+constexpr int kRedRow = 16 * 9 + 8;          // padded row of the deposit reduction buffer (doubles): 16 segments of 8 (+1)
 
 // ---- TMA (bulk async copy) helpers: global -> shared, completion on an mbarrier ------------------
 
@@ -65,9 +65,15 @@ __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
 // coalesced streaming stores straight from registers.  3-4 CTAs are resident per SM.
 
 constexpr int kMaxStages = 8;
+#ifndef IPIC_MINB_DEP
+#define IPIC_MINB_DEP 5          // resident CTAs per SM the deposit variants are compiled for (register cap 65536/128/N)
+#endif
+#ifndef IPIC_MINB_NODEP
+#define IPIC_MINB_NODEP 7
+#endif
 
 template<int ITEMS, bool INTERP, bool DEPOSIT, bool MIGRATE, bool PUSH>
-__global__ void __launch_bounds__(kBlock, DEPOSIT ? 3 : 4)
+__global__ void __launch_bounds__(kBlock, DEPOSIT ? IPIC_MINB_DEP : IPIC_MINB_NODEP)
 k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, const int64_t* __restrict__ cellStart,
        const int* __restrict__ countIn, int* __restrict__ countOut, int* __restrict__ nLeave,
        unsigned char* __restrict__ tag, const double* __restrict__ fieldEB, double* __restrict__ cellJ,
@@ -84,11 +90,13 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	const int cx = xy / g.ny, cy = xy - cx * g.ny, cz = g.z0 + zl;
 	const int cell = xy * g.lzs + zl + g.ghost;
 
-	extern __shared__ __align__(128) double sTile[];             // stages x TILE_DOUBLES (reused by the deposit reduction)
+	extern __shared__ __align__(128) double sTile[];             // stages x TILE_DOUBLES
 	__shared__ uint64_t sFull[kMaxStages];
 	__shared__ int sCnt[2][ITEMS * kWarps];                      // per (item, warp): stayers | leavers << 16
 	__shared__ alignas(16) double sCorner[48];
 	__shared__ uint64_t sBar;
+	__shared__ double sRed[DEPOSIT ? 8 * kRedRow : 1];           // deposit reduction: 8 sums x 128 partials per pass
+	__shared__ double sJ[24];                                    // the cell's 8x3 corner sums
 
 	const int n = countIn[cell];
 	const int64_t base = cellStart[cell];
@@ -97,6 +105,7 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	double* __restrict__ dst = out.d + (base << 3);
 	const int nTiles = (n + TILE - 1) / TILE;
 
+	if (DEPOSIT && tid < 24) sJ[tid] = 0.0;
 	if (tid == 0) {
 		for (int s = 0; s < stages; s++) mbar_init(&sFull[s], 1);
 		if (INTERP && PUSH) mbar_init(&sBar, 1);
@@ -137,132 +146,155 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 
 	if (INTERP && PUSH && n > 0) mbar_wait(&sBar, 0);
 
-	double acc[DEPOSIT ? 24 : 1];
-	if (DEPOSIT) {
-		#pragma unroll
-		for (int a = 0; a < 24; a++) acc[a] = 0.0;
-	}
-
 	int kept = 0, left = 0, par = 0;
-	int stage = 0; uint32_t phase = 0;
+	uint32_t phase = 0;
 	const unsigned lt = (1u << lane) - 1u;
-	for (int t = 0; t < nTiles; t++) {
-		const int c0 = t * TILE;
-		double px[ITEMS], py[ITEMS], pz[ITEMS], vx[ITEMS], vy[ITEMS], vz[ITEMS], pq[ITEMS], pm[ITEMS];
-		unsigned code[ITEMS];
-		mbar_wait(&sFull[stage], phase);
-		const double* tile = sTile + stage * TILE_DOUBLES;
-		#pragma unroll
-		for (int k = 0; k < ITEMS; k++) {
-			if (c0 + k * kBlock + tid < n) {
-				const double* p = tile + ((k * kWarps + warp) << 8) + lane;
-				px[k] = p[0]; py[k] = p[32]; pz[k] = p[64];
-				vx[k] = p[96]; vy[k] = p[128]; vz[k] = p[160];
-				pq[k] = p[192]; pm[k] = p[224];
-			}
-		}
-		#pragma unroll
-		for (int k = 0; k < ITEMS; k++) {
-			const int idx = c0 + k * kBlock + tid;
-			code[k] = kTagNone;
-			if (idx < n) {
-				if (DEPOSIT) {
-					// projectToDensityField weights (reference cell.h:810-816); corner (a,b,c) of this cell is the
-					// node the reference reaches with (i,j,k) = (-a,-b,-c).  The per-cell sums are accumulated in
-					// a different order than the reference's sequential loop anyway, so this part uses a
-					// reciprocal multiply and FMAs (J is compared at 1e-12, not bit for bit).
-					const double rx = (px[k] - org[0]) * g.iw[0], ry = (py[k] - org[1]) * g.iw[1], rz = (pz[k] - org[2]) * g.iw[2];
-					const double ox = 1.0 - rx, oy = 1.0 - ry, oz = 1.0 - rz;
-					const double jx = pq[k] * vx[k], jy = pq[k] * vy[k], jz = pq[k] * vz[k];
-					const double wxy[4] = { ox * oy, ox * ry, rx * oy, rx * ry };
-					#pragma unroll
-					for (int ab = 0; ab < 4; ab++) {
-						const double f0 = wxy[ab] * oz, f1 = wxy[ab] * rz;
-						const int o = ab * 6;
-						acc[o] = __fma_rn(jx, f0, acc[o]); acc[o + 1] = __fma_rn(jy, f0, acc[o + 1]); acc[o + 2] = __fma_rn(jz, f0, acc[o + 2]);
-						acc[o + 3] = __fma_rn(jx, f1, acc[o + 3]); acc[o + 4] = __fma_rn(jy, f1, acc[o + 4]); acc[o + 5] = __fma_rn(jz, f1, acc[o + 5]);
+
+	// The cell is worked through in batches of `stages` tiles (normally one batch = the whole cell).
+	for (int tb = 0; tb < nTiles; tb += stages) {
+		const int nb = min(stages, nTiles - tb);
+
+		if (DEPOSIT) {
+			// ---- phase A: current deposit of the batch (pre-push state), then a block reduction --------
+			// Kept apart from the push so that the 24 accumulators are dead while the mover runs: one
+			// kernel, one pass over HBM, but ~100 instead of ~160 registers (5 instead of 3 CTAs per SM).
+			double acc[24];
+			#pragma unroll
+			for (int a = 0; a < 24; a++) acc[a] = 0.0;
+			for (int b = 0; b < nb; b++) {
+				mbar_wait(&sFull[b], phase);
+				const double* tile = sTile + b * TILE_DOUBLES;
+				#pragma unroll
+				for (int k = 0; k < ITEMS; k++) {
+					if ((tb + b) * TILE + k * kBlock + tid < n) {
+						const double* p = tile + ((k * kWarps + warp) << 8) + lane;
+						// projectToDensityField weights (reference cell.h:810-816); corner (a,b,c) of this cell is the
+						// node the reference reaches with (i,j,k) = (-a,-b,-c).  The per-cell sums are accumulated in
+						// a different order than the reference's sequential loop anyway, so this part uses a
+						// reciprocal multiply and FMAs (J is compared at 1e-12, not bit for bit).
+						const double rx = (p[0] - org[0]) * g.iw[0], ry = (p[32] - org[1]) * g.iw[1], rz = (p[64] - org[2]) * g.iw[2];
+						const double ox = 1.0 - rx, oy = 1.0 - ry, oz = 1.0 - rz;
+						const double q = p[192];
+						const double jx = q * p[96], jy = q * p[128], jz = q * p[160];
+						const double wxy[4] = { ox * oy, ox * ry, rx * oy, rx * ry };
+						#pragma unroll
+						for (int ab = 0; ab < 4; ab++) {
+							const double f0 = wxy[ab] * oz, f1 = wxy[ab] * rz;
+							const int o = ab * 6;
+							acc[o] = __fma_rn(jx, f0, acc[o]); acc[o + 1] = __fma_rn(jy, f0, acc[o + 1]); acc[o + 2] = __fma_rn(jz, f0, acc[o + 2]);
+							acc[o + 3] = __fma_rn(jx, f1, acc[o + 3]); acc[o + 4] = __fma_rn(jy, f1, acc[o + 4]); acc[o + 5] = __fma_rn(jz, f1, acc[o + 5]);
+						}
 					}
 				}
-				if (INTERP && PUSH) {
-					// fractional position in the cell (reference cell.h:933), kept as a true division: bit-exact
-					const double rx = (px[k] - org[0]) / g.w[0], ry = (py[k] - org[1]) / g.w[1], rz = (pz[k] - org[2]) / g.w[2];
-					const Vec3 E = trilinear(sCorner, 6, rx, ry, rz, g.vol);
-					const Vec3 B = trilinear(sCorner + 3, 6, rx, ry, rz, g.vol);
-					push_with_fields(g, px[k], py[k], pz[k], vx[k], vy[k], vz[k], pm[k], E, B);
+			}
+			// deterministic block reduction, 8 of the 24 sums per pass: thread (seg, i) parks its partial at
+			// column seg*9+i (conflict-free), then thread (row, seg) adds the 8 partials of its segment in
+			// fixed order and the 16 segments of a row are combined with 4 shuffles
+			#pragma unroll
+			for (int pass = 0; pass < 3; pass++) {
+				#pragma unroll
+				for (int r = 0; r < 8; r++) sRed[r * kRedRow + (tid >> 3) * 9 + (tid & 7)] = acc[pass * 8 + r];
+				__syncthreads();
+				{
+					const int row = tid >> 4, seg = tid & 15;
+					const double* r = sRed + row * kRedRow + seg * 9;
+					double v = r[0];
+					#pragma unroll
+					for (int i = 1; i < 8; i++) v += r[i];
+					v += __shfl_xor_sync(0xffffffffu, v, 1);
+					v += __shfl_xor_sync(0xffffffffu, v, 2);
+					v += __shfl_xor_sync(0xffffffffu, v, 4);
+					v += __shfl_xor_sync(0xffffffffu, v, 8);
+					if (seg == 0) sJ[pass * 8 + row] += v;
 				}
-				if (!INTERP && PUSH) {
-					Vec3 E, B;
-					dipole_field(g, px[k], py[k], pz[k], E, B);
-					push_with_fields(g, px[k], py[k], pz[k], vx[k], vy[k], vz[k], pm[k], E, B);
-				}
-				if (PUSH) code[k] = MIGRATE ? classify(g, cx, cy, cz, ctr, px[k], py[k], pz[k], vx[k], vy[k], vz[k]) : 13u;
+				__syncthreads();
 			}
 		}
 
-		// stable compaction: order index of an element is k*kBlock + tid
-		unsigned bs[ITEMS], bl[ITEMS];
-		if (PUSH) {
+		// ---- phase B: push, classify, compact, store ------------------------------------------------
+		for (int b = 0; b < nb; b++) {
+			const int t = tb + b;
+			const int c0 = t * TILE;
+			if (!PUSH) {
+				// deposit-only pass: the stage is free once phase A has read it (the reduction's barriers are behind us)
+				if (tid == 0 && t + stages < nTiles) issue(t + stages, b);
+				continue;
+			}
+			double px[ITEMS], py[ITEMS], pz[ITEMS], vx[ITEMS], vy[ITEMS], vz[ITEMS], pq[ITEMS], pm[ITEMS];
+			unsigned code[ITEMS];
+			if (!DEPOSIT) mbar_wait(&sFull[b], phase);
+			const double* tile = sTile + b * TILE_DOUBLES;
+			#pragma unroll
+			for (int k = 0; k < ITEMS; k++) {
+				if (c0 + k * kBlock + tid < n) {
+					const double* p = tile + ((k * kWarps + warp) << 8) + lane;
+					px[k] = p[0]; py[k] = p[32]; pz[k] = p[64];
+					vx[k] = p[96]; vy[k] = p[128]; vz[k] = p[160];
+					pq[k] = p[192]; pm[k] = p[224];
+				}
+			}
+			#pragma unroll
+			for (int k = 0; k < ITEMS; k++) {
+				const int idx = c0 + k * kBlock + tid;
+				code[k] = kTagNone;
+				if (idx < n) {
+					if (INTERP) {
+						// fractional position in the cell (reference cell.h:933), kept as a true division: bit-exact
+						const double rx = (px[k] - org[0]) / g.w[0], ry = (py[k] - org[1]) / g.w[1], rz = (pz[k] - org[2]) / g.w[2];
+						const Vec3 E = trilinear(sCorner, 6, rx, ry, rz, g.vol);
+						const Vec3 B = trilinear(sCorner + 3, 6, rx, ry, rz, g.vol);
+						push_with_fields(g, px[k], py[k], pz[k], vx[k], vy[k], vz[k], pm[k], E, B);
+					} else {
+						Vec3 E, B;
+						dipole_field(g, px[k], py[k], pz[k], E, B);
+						push_with_fields(g, px[k], py[k], pz[k], vx[k], vy[k], vz[k], pm[k], E, B);
+					}
+					code[k] = MIGRATE ? classify(g, cx, cy, cz, ctr, px[k], py[k], pz[k], vx[k], vy[k], vz[k]) : 13u;
+				}
+			}
+
+			// stable compaction: order index of an element is k*kBlock + tid
+			unsigned bs[ITEMS], bl[ITEMS];
 			#pragma unroll
 			for (int k = 0; k < ITEMS; k++) {
 				bs[k] = __ballot_sync(0xffffffffu, code[k] == 13u);
 				bl[k] = __ballot_sync(0xffffffffu, code[k] < 27u && code[k] != 13u);
 				if (lane == 0) sCnt[par][k * kWarps + warp] = __popc(bs[k]) | (__popc(bl[k]) << 16);
 			}
-		}
-		__syncthreads();                                         // every thread has its tile in registers: stage is free
-		if (tid == 0 && t + stages < nTiles) issue(t + stages, stage);
-		if (++stage == stages) { stage = 0; phase ^= 1; }
-		if (!PUSH) continue;                                     // deposit-only pass: nothing is written back
+			__syncthreads();                                     // every thread has its tile in registers: stage is free
+			if (tid == 0 && t + stages < nTiles) issue(t + stages, b);
 
-		int run = 0, mine[ITEMS];
-		#pragma unroll
-		for (int k = 0; k < ITEMS; k++)
+			int run = 0, mine[ITEMS];
 			#pragma unroll
-			for (int w = 0; w < kWarps; w++) {
-				if (w == warp) mine[k] = run;
-				run += sCnt[par][k * kWarps + w];
-			}
-		#pragma unroll
-		for (int k = 0; k < ITEMS; k++) {
-			const bool st = code[k] == 13u, lv = code[k] < 27u && code[k] != 13u;
-			if (st || lv) {
-				int d;
-				if (st) d = kept + (mine[k] & 0xffff) + __popc(bs[k] & lt);
-				else {
-					d = cap - 1 - (left + (mine[k] >> 16) + __popc(bl[k] & lt));
-					tag[base + d] = (unsigned char)code[k];
+			for (int k = 0; k < ITEMS; k++)
+				#pragma unroll
+				for (int w = 0; w < kWarps; w++) {
+					if (w == warp) mine[k] = run;
+					run += sCnt[par][k * kWarps + w];
 				}
-				double* q = dst + ((int64_t)(d >> 5) << 8) + (d & 31);
-				st_stream(q, px[k]); st_stream(q + 32, py[k]); st_stream(q + 64, pz[k]);
-				st_stream(q + 96, vx[k]); st_stream(q + 128, vy[k]); st_stream(q + 160, vz[k]);
-				st_stream(q + 192, pq[k]); st_stream(q + 224, pm[k]);
+			#pragma unroll
+			for (int k = 0; k < ITEMS; k++) {
+				const bool st = code[k] == 13u, lv = code[k] < 27u && code[k] != 13u;
+				if (st || lv) {
+					int d;
+					if (st) d = kept + (mine[k] & 0xffff) + __popc(bs[k] & lt);
+					else {
+						d = cap - 1 - (left + (mine[k] >> 16) + __popc(bl[k] & lt));
+						tag[base + d] = (unsigned char)code[k];
+					}
+					double* q = dst + ((int64_t)(d >> 5) << 8) + (d & 31);
+					st_stream(q, px[k]); st_stream(q + 32, py[k]); st_stream(q + 64, pz[k]);
+					st_stream(q + 96, vx[k]); st_stream(q + 128, vy[k]); st_stream(q + 160, vz[k]);
+					st_stream(q + 192, pq[k]); st_stream(q + 224, pm[k]);
+				}
 			}
+			kept += run & 0xffff; left += run >> 16;
+			par ^= 1;
 		}
-		kept += run & 0xffff; left += run >> 16;
-		par ^= 1;
+		phase ^= 1;
 	}
 	if (PUSH && tid == 0) { countOut[cell] = kept; nLeave[cell] = left; }
-
-	if (DEPOSIT) {
-		// deterministic block reduction of the 8x3 corner sums through shared memory (the tile stages are
-		// idle by now): 96 threads each add 32 partials of one (row, warp) segment in fixed order, then the
-		// 4 segments of a row are combined by two shuffles
-		double* sRed = sTile;
-		__syncthreads();
-		#pragma unroll
-		for (int a = 0; a < 24; a++) sRed[a * kRedStride + warp * 33 + lane] = acc[a];
-		__syncthreads();
-		if (tid < 96) {
-			const int row = tid >> 2, seg = tid & 3;
-			const double* r = sRed + row * kRedStride + seg * 33;
-			double v = r[0];
-			#pragma unroll
-			for (int i = 1; i < 32; i++) v += r[i];
-			v += __shfl_xor_sync(0xffffffffu, v, 1);
-			v += __shfl_xor_sync(0xffffffffu, v, 2);
-			if (seg == 0) cellJ[(((int64_t)cx * g.ny + cy) * g.nz + cz) * 24 + row] = v;      // indexed by GLOBAL cell id
-		}
-	}
+	if (DEPOSIT && tid < 24) cellJ[(((int64_t)cx * g.ny + cy) * g.nz + cz) * 24 + tid] = sJ[tid];      // indexed by GLOBAL cell id
 }
 
 // ---- import: append the 26 incoming outboxes in canonical order (reference cell.h:1195-1310) ------
@@ -503,9 +535,8 @@ void launch_selftest_division(uint64_t n, uint64_t seed, unsigned long long* bad
 
 // dynamic shared memory of one CTA: the tile stages, and at least the deposit reduction buffer
 static size_t move_smem_bytes(int items, int stages, bool deposit) {
-	size_t b = (size_t)stages * items * kBlock * kFields * sizeof(double);
-	if (deposit) b = std::max(b, (size_t)24 * kRedStride * sizeof(double));
-	return b;
+	(void)deposit;
+	return (size_t)stages * items * kBlock * kFields * sizeof(double);
 }
 
 template<int ITEMS, bool INTERP, bool DEPOSIT, bool MIGRATE, bool PUSH>
