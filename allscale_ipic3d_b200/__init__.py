@@ -5,8 +5,8 @@ The product is the C-ABI shared library ``lib/libipic3d_b200.so`` (hand-written 
 ``host/``.  This Python package is only the thin ctypes binding used by tests and ``bench.py``.
 There is no CPU fallback: without the built library or without a CUDA device every call fails loudly.
 """
-from .capi import (Context, IpicError, Props, lib_path, load_library,  # noqa: F401
+from .capi import (Context, Group, IpicError, Props, lib_path, load_library,  # noqa: F401
                    MOVER_DIPOLE_ANALYTIC, MOVER_INTERPOLATED, PROJECT_CURRENT, SOLVER_FORWARD,
                    SOLVER_LEAPFROG, UPDATE_BOUNDARIES, SKIP_MIGRATION)
 
-__all__ = ["Context", "IpicError", "Props", "lib_path", "load_library"]
+__all__ = ["Context", "Group", "IpicError", "Props", "lib_path", "load_library"]

@@ -20,6 +20,7 @@ API_SYMBOLS = [
     "ipic_set_headroom", "ipic_comm_unique_id", "ipic_comm_init", "ipic_upload_cells", "ipic_download_cells",
     "ipic_cell_counts", "ipic_total_particles", "ipic_upload_fields", "ipic_download_fields", "ipic_step",
     "ipic_step_async", "ipic_sync", "ipic_count_misplaced", "ipic_profile_reset", "ipic_profile_get", "ipic_selftest",
+    "ipic_set_exchange_capacity", "ipic_group_create", "ipic_group_step", "ipic_relayout_count",
 ]
 
 
@@ -99,12 +100,15 @@ def _up(a):
 class Context:
     """One z-slab of a universe on one GPU (``ipic_ctx``).  Single GPU: rank 0 of 1."""
 
-    def __init__(self, props, device=0, rank=0, nranks=1):
+    def __init__(self, props, device=0, rank=0, nranks=1, _handle=None):
         self.lib = load_library()
         self.props = Props.from_other(props)
         self.rank, self.nranks = rank, nranks
         self.h = C.c_void_p()
-        self._ck(self.lib.ipic_create_slab(C.byref(self.props), C.c_int(device), C.c_int(rank), C.c_int(nranks), C.byref(self.h)))
+        if _handle is not None:
+            self.h = C.c_void_p(_handle)
+        else:
+            self._ck(self.lib.ipic_create_slab(C.byref(self.props), C.c_int(device), C.c_int(rank), C.c_int(nranks), C.byref(self.h)))
         nz = int(self.props.size[2]) // nranks
         self.owned_cells = int(self.props.size[0] * self.props.size[1]) * nz
 
@@ -143,8 +147,16 @@ class Context:
         self._ck(self.lib.ipic_comm_init(self.h, C.c_char_p(unique_id)))
 
     # -- state --
+    def set_exchange_capacity(self, particles):
+        self._ck(self.lib.ipic_set_exchange_capacity(self.h, C.c_int64(particles)))
+
     def set_headroom(self, slack, min_pad=64):
         self._ck(self.lib.ipic_set_headroom(self.h, C.c_double(slack), C.c_int64(min_pad)))
+
+    def relayout_count(self):
+        t = C.c_uint64(0)
+        self._ck(self.lib.ipic_relayout_count(self.h, C.byref(t)))
+        return int(t.value)
 
     def upload_cells(self, counts, aos):
         counts = np.ascontiguousarray(counts, dtype=np.uint64)
@@ -216,6 +228,100 @@ class Context:
         a, b, n = C.c_double(0), C.c_double(0), C.c_uint64(0)
         self._ck(self.lib.ipic_profile_get(self.h, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, int(n.value)
+
+
+class Group:
+    """All z-slabs of a universe in ONE process (``ipic_group_create``): rank r on ``devices[r]`` (devices may
+    repeat), exchange by peer copies.  Host arrays are given / returned for the whole universe."""
+
+    def __init__(self, props, devices):
+        self.lib = load_library()
+        self.props = Props.from_other(props)
+        n = len(devices)
+        self.nz = int(self.props.size[2])
+        if self.nz % n:
+            raise ValueError("nz=%d is not divisible by %d slabs" % (self.nz, n))
+        self.lz = self.nz // n
+        handles = (C.c_void_p * n)()
+        devs = (C.c_int * n)(*devices)
+        rc = self.lib.ipic_group_create(C.byref(self.props), devs, C.c_int(n), handles)
+        if rc:
+            raise IpicError(rc, self.lib.ipic_last_error().decode())
+        self._handles = handles
+        self.members = [Context(self.props, devices[r], r, n, _handle=handles[r]) for r in range(n)]
+
+    def close(self):
+        for m in self.members:
+            m.close()
+        self.members = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _slab_index(self, r):
+        """Indices of rank r's cells in the global flatten, in slab order (x*ny + y)*lz + zl."""
+        nxy = int(self.props.size[0] * self.props.size[1])
+        return (np.arange(nxy)[:, None] * self.nz + r * self.lz + np.arange(self.lz)[None, :]).reshape(-1)
+
+    def upload_cells(self, counts, aos):
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        aos = np.ascontiguousarray(aos, dtype=np.float64).reshape(-1, 8)
+        start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        for r, m in enumerate(self.members):
+            idx = self._slab_index(r)
+            rows = np.concatenate([np.arange(start[i], start[i + 1]) for i in idx]) if len(idx) else np.zeros(0, dtype=np.int64)
+            m.upload_cells(counts[idx], aos[rows.astype(np.int64)])
+
+    def download_cells(self):
+        ncell = self.props.ncells
+        counts = np.zeros(ncell, dtype=np.uint64)
+        parts = [None] * ncell
+        for r, m in enumerate(self.members):
+            c, a = m.download_cells()
+            idx = self._slab_index(r)
+            counts[idx] = c
+            s = np.concatenate([[0], np.cumsum(c)]).astype(np.int64)
+            for k, i in enumerate(idx):
+                parts[i] = a[s[k]:s[k + 1]]
+        aos = np.concatenate(parts) if ncell else np.zeros((0, 8))
+        return counts, aos.reshape(-1, 8)
+
+    def cell_counts(self):
+        counts = np.zeros(self.props.ncells, dtype=np.uint64)
+        for r, m in enumerate(self.members):
+            counts[self._slab_index(r)] = m.cell_counts()
+        return counts
+
+    def upload_fields(self, field=None, bcfield=None, density=None):
+        for m in self.members:                      # the field grids are replicated on every slab
+            m.upload_fields(field, bcfield, density)
+
+    def download_fields(self, rank=0):
+        return self.members[rank].download_fields()
+
+    def set_headroom(self, slack, min_pad=64):
+        for m in self.members:
+            m.set_headroom(slack, min_pad)
+
+    def set_exchange_capacity(self, particles):
+        for m in self.members:
+            m.set_exchange_capacity(particles)
+
+    def step(self, n=1, flags=0):
+        a, b = C.c_double(0), C.c_double(0)
+        rc = self.lib.ipic_group_step(self._handles, C.c_int(len(self.members)), C.c_uint64(n), C.c_uint32(flags), C.byref(a), C.byref(b))
+        if rc:
+            raise IpicError(rc, self.lib.ipic_last_error().decode())
+        return a.value, b.value
+
+    def count_misplaced(self):
+        return sum(m.count_misplaced() for m in self.members)
+
+    def relayout_count(self):
+        return sum(m.relayout_count() for m in self.members)
 
 
 def selftest(n=1 << 22, seed=1, device=0):

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -38,6 +39,8 @@ inline int64_t alignUp(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 } // namespace
 
+struct ipic_group;
+
 struct ipic_ctx {
 	int device = 0, rank = 0, nranks = 1;
 	ipic_props props{};
@@ -54,7 +57,7 @@ struct ipic_ctx {
 	int* dStay = nullptr;                          // stayers per cell after the mover (head of segment, other generation)
 	int* dLeave = nullptr;                         // outbox entries per local cell
 	unsigned char* dTag = nullptr;                 // direction tag per slot (outbox entries only)
-	int* dStop = nullptr;                          // [0] stop, [1] first failing step, [2] overflow seen
+	int* dStop = nullptr;                          // [0] stop, [1] first failing step, [2] cell overflow seen in this import pass, [3] exchange failure (1 face message full on this rank, 2 unusable message received)
 	bool haveCells = false;
 	int64_t meanPopulation = 0;                    // particles per owned cell at upload (drives the mover's tile shape)
 	double slack = 0.25;                           // head-room per cell as a fraction of its population
@@ -74,13 +77,33 @@ struct ipic_ctx {
 
 	// measurement
 	bool profiling = false;
-	std::vector<cudaEvent_t> events;               // triples: before mover, after mover, after import
+	std::vector<cudaEvent_t> events;               // pairs (start, end) around the mover / import launches
+	std::vector<int> eventKind;                    // per pair: 0 mover, 1 import
 	size_t eventsUsed = 0;
 	double moverMs = 0, importMs = 0;
 	uint64_t launches = 0;
+	uint64_t relayouts = 0;                        // cell-segment overflows repaired so far
 
+	// z-slab exchange (nranks > 1): NCCL communicator (one process per GPU) or an in-process group
 	ipic_comm* comm = nullptr;
+	std::shared_ptr<ipic_group> group;
+	cudaStream_t commStream = nullptr;
+	cudaEvent_t evPacked = nullptr, evRecv = nullptr, evMoved = nullptr, evJ = nullptr;
+	int64_t userMsgCap = 0;                        // ipic_set_exchange_capacity (0 = automatic)
+	int64_t facePopulation = 0;                    // particles in the fuller of the two boundary planes at upload
+	bool exchangeDirty = true;                     // message capacity must be (re)negotiated before the next step
+	int msgCap = 0;                                // agreed capacity of a face message, in particles
+	size_t msgBytes = 0;
+	char* sendMsg[2] = { nullptr, nullptr };       // [0] face 0 -> slab below, [1] face 1 -> slab above
+	char* recvMsg[2] = { nullptr, nullptr };       // [0] from the slab below, [1] from the slab above
+	int* dFaceCnt = nullptr;
+	int64_t* dNegotiate = nullptr;                 // nranks x int64 scratch
+	int* hStop = nullptr;                          // pinned mirror of dStop, refreshed after every slab step
+	cudaEvent_t evStepDone = nullptr;
 };
+
+// contexts of one process that form a complete set of slabs and exchange by peer copies
+struct ipic_group { std::vector<ipic_ctx*> members; };
 
 namespace {
 
@@ -105,22 +128,12 @@ int64_t capacityFor(const ipic_ctx* c, int64_t n) {
 	return alignUp(n + std::max<int64_t>((int64_t)std::ceil((double)n * c->slack), c->minPad), kSlotAlign);
 }
 
-// segment layout for the local cell array (owned cells from `need`, ghost cells sized like the
-// largest owned cell of the adjacent plane's average outbox expectation)
-void buildLayout(const ipic_ctx* c, const std::vector<int64_t>& needOwned, std::vector<int64_t>& start) {
+// segment layout of the slab's cells: capacity for the current population plus head-room
+void buildLayout(const ipic_ctx* c, const std::vector<int64_t>& need, std::vector<int64_t>& start) {
 	const Geometry& g = c->g;
 	start.assign((size_t)g.ncellsLocal + 1, 0);
-	int64_t maxOwned = 0;
-	for (int64_t v : needOwned) maxOwned = std::max(maxOwned, v);
-	const int64_t ghostCap = alignUp(std::max<int64_t>(maxOwned / 2, 256), kSlotAlign);
 	int64_t pos = 0;
-	for (int xy = 0; xy < g.nx * g.ny; xy++)
-		for (int zs = 0; zs < g.lzs; zs++) {
-			const int cell = xy * g.lzs + zs;
-			start[cell] = pos;
-			const bool isGhost = g.ghost && (zs == 0 || zs == g.lzs - 1);
-			pos += isGhost ? ghostCap : capacityFor(c, needOwned[(size_t)xy * g.lz + (zs - g.ghost)]);
-		}
+	for (int cell = 0; cell < g.ncellsLocal; cell++) { start[(size_t)cell] = pos; pos += capacityFor(c, need[(size_t)cell]); }
 	start[(size_t)g.ncellsLocal] = pos;
 }
 
@@ -134,12 +147,9 @@ int ensureStage(ipic_ctx* c, int64_t doubles) {
 }
 
 int fetchOwnedCounts(ipic_ctx* c, const int* dArray, std::vector<int>& out) {
-	std::vector<int> local((size_t)c->g.ncellsLocal);
-	CK(cudaMemcpyAsync(local.data(), dArray, local.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-	CK(cudaStreamSynchronize(c->stream));
 	out.resize((size_t)ownedCells(c));
-	for (int xy = 0; xy < c->g.nx * c->g.ny; xy++)
-		for (int zl = 0; zl < c->g.lz; zl++) out[(size_t)xy * c->g.lz + zl] = local[(size_t)xy * c->g.lzs + zl + c->g.ghost];
+	CK(cudaMemcpyAsync(out.data(), dArray, out.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
 	return IPIC_OK;
 }
 
@@ -149,9 +159,7 @@ void fillGeometry(ipic_ctx* c) {
 	g.nx = (int)p.size[0]; g.ny = (int)p.size[1]; g.nz = (int)p.size[2];
 	g.lz = g.nz / c->nranks;
 	g.z0 = c->rank * g.lz;
-	g.ghost = c->nranks > 1 ? 1 : 0;
-	g.lzs = g.lz + 2 * g.ghost;
-	g.ncellsLocal = g.nx * g.ny * g.lzs;
+	g.ncellsLocal = g.nx * g.ny * g.lz;
 	for (int a = 0; a < 3; a++) {
 		g.w[a] = p.cellWidth[a];
 		g.hw[a] = p.cellWidth[a] / 2.0;
@@ -187,14 +195,43 @@ cudaEvent_t nextEvent(ipic_ctx* c) {
 }
 
 int drainProfile(ipic_ctx* c) {
-	for (size_t i = 0; i + 2 < c->eventsUsed; i += 3) {
-		float a = 0, b = 0;
+	for (size_t i = 0; i + 1 < c->eventsUsed; i += 2) {
+		float a = 0;
 		CK(cudaEventElapsedTime(&a, c->events[i], c->events[i + 1]));
-		CK(cudaEventElapsedTime(&b, c->events[i + 1], c->events[i + 2]));
-		c->moverMs += a; c->importMs += b;
+		(c->eventKind[i / 2] == 0 ? c->moverMs : c->importMs) += a;
 	}
 	c->eventsUsed = 0;
+	c->eventKind.clear();
 	return IPIC_OK;
+}
+
+// CUDA-event bracket around a group of launches on the context's stream (only while profiling)
+struct ProfSpan {
+	ipic_ctx* c; cudaEvent_t end = nullptr;
+	ProfSpan(ipic_ctx* ctx, int kind) : c(ctx) {
+		if (!c->profiling) return;
+		cudaEvent_t start = nextEvent(c); end = nextEvent(c);
+		c->eventKind.push_back(kind);
+		cudaEventRecord(start, c->stream);
+	}
+	~ProfSpan() { if (end) cudaEventRecord(end, c->stream); }
+};
+
+FaceMsg faceView(const ipic_ctx* c, char* base) {
+	const int nxy = c->g.nx * c->g.ny;
+	FaceMsg m;
+	m.offsets = reinterpret_cast<int*>(base);
+	const size_t offP = (size_t)alignUp((int64_t)(nxy + 1) * 4, 128);
+	m.particles = reinterpret_cast<double*>(base + offP);
+	m.tags = reinterpret_cast<unsigned char*>(base + offP + (size_t)c->msgCap * 64);
+	m.cap = c->msgCap;
+	return m;
+}
+
+// where the import kernel finds the outboxes of the cells beyond the slab's first / last plane
+void setImportSources(const ipic_ctx* c, ImportArgs& ia) {
+	ia.slab = c->nranks > 1;
+	if (ia.slab) { ia.fromDown = faceView(c, c->recvMsg[0]); ia.fromUp = faceView(c, c->recvMsg[1]); }
 }
 
 // Re-establish a valid layout after the import of `failedStep` ran out of room: the generation that
@@ -215,7 +252,7 @@ int relayoutAfterOverflow(ipic_ctx* c, int outGen, int failedStep) {
 	int64_t* dNewStart = nullptr;
 	CK(cudaMalloc(&dNewStart, newStart.size() * sizeof(int64_t)));
 	CK(cudaMemcpyAsync(dNewStart, newStart.data(), newStart.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-	CK(cudaMemsetAsync(c->dStop, 0, 3 * sizeof(int), c->stream));
+	CK(cudaMemsetAsync(c->dStop, 0, 4 * sizeof(int), c->stream));
 	int big = 0x7fffffff;
 	CK(cudaMemcpyAsync(c->dStop + 1, &big, sizeof(int), cudaMemcpyHostToDevice, c->stream));
 	launch_copy_heads(c->g, c->buf[outGen], c->dCellStart, nb[outGen], dNewStart, c->dStay, c->stream);
@@ -223,10 +260,11 @@ int relayoutAfterOverflow(ipic_ctx* c, int outGen, int failedStep) {
 	ia.g = c->g; ia.src = c->buf[outGen]; ia.srcStart = c->dCellStart; ia.srcLeave = c->dLeave; ia.tag = c->dTag;
 	ia.dst = nb[outGen]; ia.dstStart = dNewStart; ia.stay = c->dStay; ia.dstCount = c->dCount;
 	ia.reserveOwnOutbox = 0; ia.stopFlag = c->dStop; ia.stepIndex = failedStep; ia.zBegin = 0; ia.zCount = c->g.lz;
-	launch_import(ia, c->stream);
+	setImportSources(c, ia);
+	launch_import(ia, true, c->stream);
 	c->launches += 3;
 	CK(cudaStreamSynchronize(c->stream));
-	int stop[3];
+	int stop[4];
 	CK(cudaMemcpy(stop, c->dStop, sizeof stop, cudaMemcpyDeviceToHost));
 	// swap in the new storage
 	freeParticleBuffers(c);
@@ -274,8 +312,8 @@ int ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, 
 	CK(cudaMemset(c->dCount, 0, (size_t)g.ncellsLocal * sizeof(int)));
 	CK(cudaMemset(c->dStay, 0, (size_t)g.ncellsLocal * sizeof(int)));
 	CK(cudaMemset(c->dLeave, 0, (size_t)g.ncellsLocal * sizeof(int)));
-	CK(cudaMalloc(&c->dStop, 3 * sizeof(int)));
-	int stop[3] = { 0, 0x7fffffff, 0 };
+	CK(cudaMalloc(&c->dStop, 4 * sizeof(int)));
+	int stop[4] = { 0, 0x7fffffff, 0, 0 };
 	CK(cudaMemcpy(c->dStop, stop, sizeof stop, cudaMemcpyHostToDevice));
 	c->nField = (int64_t)(g.nx + 3) * (g.ny + 3) * (g.nz + 3);
 	c->nBc = (int64_t)(g.nx + 2) * (g.ny + 2) * (g.nz + 2);
@@ -291,6 +329,14 @@ int ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, 
 	CK(cudaMemset(c->dJ, 0, (size_t)c->nJ * 3 * sizeof(double)));
 	CK(cudaMemset(c->dCellJ, 0, (size_t)g.nx * g.ny * g.nz * 24 * sizeof(double)));
 	CK(cudaMalloc(&c->dAosStart, ((size_t)ownedCells(c) + 1) * sizeof(int64_t)));
+	if (nranks > 1) {
+		CK(cudaStreamCreateWithFlags(&c->commStream, cudaStreamNonBlocking));
+		for (cudaEvent_t* e : { &c->evPacked, &c->evRecv, &c->evMoved, &c->evJ }) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+		CK(cudaMalloc(&c->dFaceCnt, (size_t)2 * g.nx * g.ny * sizeof(int)));
+		CK(cudaMalloc(&c->dNegotiate, (size_t)nranks * sizeof(int64_t)));
+		CK(cudaMallocHost(&c->hStop, 4 * sizeof(int)));
+		CK(cudaEventCreateWithFlags(&c->evStepDone, cudaEventDisableTiming));
+	}
 	*out = c;
 	return IPIC_OK;
 }
@@ -301,7 +347,19 @@ int ipic_destroy(ipic_ctx* c) {
 	if (!c) return IPIC_OK;
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->commStream) cudaStreamSynchronize(c->commStream);
 	if (c->comm) comm_destroy(c->comm);
+	if (c->group) {
+		// the remaining members can no longer step; drop the back references
+		for (ipic_ctx*& m : c->group->members) if (m == c) m = nullptr;
+		c->group.reset();
+	}
+	for (int i = 0; i < 2; i++) { cudaFree(c->sendMsg[i]); cudaFree(c->recvMsg[i]); }
+	cudaFree(c->dFaceCnt); cudaFree(c->dNegotiate);
+	if (c->hStop) cudaFreeHost(c->hStop);
+	if (c->evStepDone) cudaEventDestroy(c->evStepDone);
+	for (cudaEvent_t e : { c->evPacked, c->evRecv, c->evMoved, c->evJ }) if (e) cudaEventDestroy(e);
+	if (c->commStream) cudaStreamDestroy(c->commStream);
 	freeParticleBuffers(c);
 	cudaFree(c->dCellStart); cudaFree(c->dCount); cudaFree(c->dStay); cudaFree(c->dLeave); cudaFree(c->dStop);
 	cudaFree(c->dEB); cudaFree(c->dBext); cudaFree(c->dBc); cudaFree(c->dJ); cudaFree(c->dCellJ);
@@ -318,6 +376,13 @@ int ipic_set_headroom(ipic_ctx* c, double slack, int64_t minPad) {
 	return IPIC_OK;
 }
 
+int ipic_set_exchange_capacity(ipic_ctx* c, int64_t particles) {
+	if (!c || particles < 0 || particles > ((int64_t)1 << 26)) return fail(IPIC_ERR_ARG, "bad exchange capacity");
+	c->userMsgCap = particles;
+	c->exchangeDirty = true;
+	return IPIC_OK;
+}
+
 int ipic_upload_cells(ipic_ctx* c, const uint64_t* counts, const double* aos) {
 	if (!c || !counts) return fail(IPIC_ERR_ARG, "null argument");
 	CK(cudaSetDevice(c->device));
@@ -328,8 +393,7 @@ int ipic_upload_cells(ipic_ctx* c, const uint64_t* counts, const double* aos) {
 		if (counts[i] > 0x3fffffffu) return fail(IPIC_ERR_ARG, "cell %d holds %llu particles (limit 2^30 per cell)", i, (unsigned long long)counts[i]);
 		need[i] = (int64_t)counts[i];
 		aosStart[i + 1] = aosStart[i] + need[i];
-		const int xy = i / c->g.lz, zl = i % c->g.lz;
-		localCount[(size_t)xy * c->g.lzs + zl + c->g.ghost] = (int)counts[i];
+		localCount[(size_t)i] = (int)counts[i];
 	}
 	const int64_t total = aosStart[nOwned];
 	if (total > 0 && !aos) return fail(IPIC_ERR_ARG, "particles_aos is null");
@@ -356,6 +420,12 @@ int ipic_upload_cells(ipic_ctx* c, const uint64_t* counts, const double* aos) {
 	CK(cudaStreamSynchronize(c->stream));     // host vectors above go out of scope
 	c->haveCells = true;
 	c->meanPopulation = total / std::max(1, nOwned);
+	if (c->nranks > 1) {
+		int64_t lo = 0, hi = 0;
+		for (int xy = 0; xy < c->g.nx * c->g.ny; xy++) { lo += need[(size_t)xy * c->g.lz]; hi += need[(size_t)xy * c->g.lz + c->g.lz - 1]; }
+		c->facePopulation = std::max(lo, hi);
+		c->exchangeDirty = true;
+	}
 	return IPIC_OK;
 }
 
@@ -434,71 +504,292 @@ int ipic_download_fields(ipic_ctx* c, double* field, double* bc, double* J) {
 	return IPIC_OK;
 }
 
-// One iteration of the time loop, enqueued on the context's stream.
-static int enqueueStep(ipic_ctx* c, uint32_t flags, int stepIndex) {
-	const bool interp = flags & IPIC_MOVER_INTERPOLATED;
-	const bool project = flags & IPIC_PROJECT_CURRENT;
-	const bool solve = flags & (IPIC_SOLVER_FORWARD | IPIC_SOLVER_LEAPFROG);
-	const bool migrate = !(flags & IPIC_SKIP_MIGRATION);
-	const int in = c->cur, out = c->cur ^ 1;
+// ---- one iteration of the time loop --------------------------------------------------------------
 
+namespace {
+
+struct StepFlags {
+	bool interp, project, solve, migrate, fuseDeposit;
+	uint32_t raw;
+	explicit StepFlags(uint32_t f) : raw(f) {
+		interp = f & IPIC_MOVER_INTERPOLATED;
+		project = f & IPIC_PROJECT_CURRENT;
+		solve = f & (IPIC_SOLVER_FORWARD | IPIC_SOLVER_LEAPFROG);
+		migrate = !(f & IPIC_SKIP_MIGRATION);
+		// The reference order is project -> boundaries/solve -> move -> import (simulator.h:189-223).  The
+		// analytic mover never reads the grid, so there the projection is fused into the mover pass and the
+		// field phase runs after it with identical results; the interpolating mover needs the new fields
+		// first, so its projection is a separate read-only pass.
+		fuseDeposit = project && !interp;
+	}
+};
+
+MoveArgs moveArgs(ipic_ctx* c, const StepFlags& f, int zBegin, int zCount) {
+	const int in = c->cur, out = c->cur ^ 1;
 	MoveArgs ma{};
 	ma.g = c->g; ma.in = c->buf[in]; ma.out = c->buf[out]; ma.cellStart = c->dCellStart;
 	ma.countIn = c->dCount; ma.countOut = c->dStay; ma.nLeave = c->dLeave; ma.tag = c->dTag;
 	ma.fieldEB = c->dEB; ma.cellJ = c->dCellJ; ma.stopFlag = c->dStop;
-	ma.zBegin = 0; ma.zCount = c->g.lz;
-	ma.interpolate = interp; ma.migrate = migrate; ma.push = true;
-
-	auto fieldPhase = [&]() {
-		if (flags & IPIC_UPDATE_BOUNDARIES) { launch_update_boundaries(c->g, c->dEB, c->dBext, c->dBc, c->dStop, c->stream); c->launches += 2; }
-		if (solve) c->launches += launch_field_solver(c->g, (flags & IPIC_SOLVER_FORWARD) != 0, c->dEB, c->dBc, c->dJ, c->dStop, c->stream);
-	};
-
-	// The reference order is project -> boundaries/solve -> move -> import (simulator.h:189-223).  The
-	// analytic mover never reads the grid, so there the projection is fused into the mover pass and the
-	// field phase runs after it with identical results; the interpolating mover needs the new fields
-	// first, so its projection is a separate read-only pass.
-	const bool fuseDeposit = project && !interp;
-	if (project && interp) {
-		MoveArgs da = ma; da.push = false; da.deposit = true; da.interpolate = false;
-		pickTileShape(c, true, da.itemsPerThread, da.stages);
-		launch_move(da, c->stream);
-		launch_gather_current(c->g, c->dCellJ, c->dJ, c->dStop, c->stream);
-		c->launches += 2;
-	}
-	if (!fuseDeposit) fieldPhase();
-
-	cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-	if (c->profiling) { e0 = nextEvent(c); e1 = nextEvent(c); e2 = nextEvent(c); cudaEventRecord(e0, c->stream); }
-	ma.deposit = fuseDeposit;
+	ma.zBegin = zBegin; ma.zCount = zCount;
+	ma.interpolate = f.interp; ma.migrate = f.migrate; ma.push = true; ma.deposit = f.fuseDeposit;
 	pickTileShape(c, ma.deposit, ma.itemsPerThread, ma.stages);
-	launch_move(ma, c->stream);
-	c->launches++;
-	if (c->profiling) cudaEventRecord(e1, c->stream);
+	return ma;
+}
 
-	if (fuseDeposit) {
+void fieldPhase(ipic_ctx* c, const StepFlags& f) {
+	if (f.raw & IPIC_UPDATE_BOUNDARIES) { launch_update_boundaries(c->g, c->dEB, c->dBext, c->dBc, c->dStop, c->stream); c->launches += 2; }
+	if (f.solve) c->launches += launch_field_solver(c->g, (f.raw & IPIC_SOLVER_FORWARD) != 0, c->dEB, c->dBc, c->dJ, c->dStop, c->stream);
+}
+
+// deposit-only pass over the given planes (the projection of the interpolating mode)
+void depositPass(ipic_ctx* c, const StepFlags& f, int zBegin, int zCount) {
+	MoveArgs da = moveArgs(c, f, zBegin, zCount);
+	da.push = false; da.deposit = true; da.interpolate = false;
+	pickTileShape(c, true, da.itemsPerThread, da.stages);
+	launch_move(da, c->stream);
+	c->launches++;
+}
+
+void importPlanes(ipic_ctx* c, int stepIndex, int zBegin, int zCount, bool commit) {
+	if (zCount <= 0) return;
+	const int out = c->cur ^ 1;
+	ImportArgs ia{};
+	ia.g = c->g; ia.src = c->buf[out]; ia.srcStart = c->dCellStart; ia.srcLeave = c->dLeave; ia.tag = c->dTag;
+	ia.dst = c->buf[out]; ia.dstStart = c->dCellStart; ia.stay = c->dStay; ia.dstCount = c->dCount;
+	ia.reserveOwnOutbox = 1; ia.stopFlag = c->dStop; ia.stepIndex = stepIndex; ia.zBegin = zBegin; ia.zCount = zCount;
+	setImportSources(c, ia);
+	launch_import(ia, commit, c->stream);
+	c->launches += commit ? 2 : 1;
+}
+
+// the whole universe on one GPU: no exchange
+int enqueueStepSingle(ipic_ctx* c, const StepFlags& f, int stepIndex) {
+	if (f.project && f.interp) {
+		depositPass(c, f, 0, c->g.lz);
 		launch_gather_current(c->g, c->dCellJ, c->dJ, c->dStop, c->stream);
 		c->launches++;
-		fieldPhase();
 	}
-
-	if (migrate) {
-		ImportArgs ia{};
-		ia.g = c->g; ia.src = c->buf[out]; ia.srcStart = c->dCellStart; ia.srcLeave = c->dLeave; ia.tag = c->dTag;
-		ia.dst = c->buf[out]; ia.dstStart = c->dCellStart; ia.stay = c->dStay; ia.dstCount = c->dCount;
-		ia.reserveOwnOutbox = 1; ia.stopFlag = c->dStop; ia.stepIndex = stepIndex; ia.zBegin = 0; ia.zCount = c->g.lz;
-		launch_import(ia, c->stream);
-		c->launches += 2;
+	if (!f.fuseDeposit) fieldPhase(c, f);
+	{
+		ProfSpan span(c, 0);
+		launch_move(moveArgs(c, f, 0, c->g.lz), c->stream);
+		c->launches++;
+	}
+	if (f.fuseDeposit) {
+		launch_gather_current(c->g, c->dCellJ, c->dJ, c->dStop, c->stream);
+		c->launches++;
+		fieldPhase(c, f);
+	}
+	if (f.migrate) {
+		ProfSpan span(c, 1);
+		importPlanes(c, stepIndex, 0, c->g.lz, true);
 	} else {
 		CK(cudaMemcpyAsync(c->dCount, c->dStay, (size_t)c->g.ncellsLocal * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
 	}
-	if (c->profiling) cudaEventRecord(e2, c->stream);
-	c->cur = out;
+	c->cur ^= 1;
 	CK(cudaGetLastError());
 	return IPIC_OK;
 }
 
-static int enqueueSteps(ipic_ctx* c, uint64_t first, uint64_t count, uint32_t flags) {
+// ---- z-slab contexts ------------------------------------------------------------------------------
+//
+// A step of a slab is enqueued in phases.  With NCCL (one process per GPU) a context runs its phases
+// back to back; an in-process group runs every phase over all members before the next one so that
+// each cross-context event wait refers to an event recorded earlier in host order.
+//
+//   BOUNDARY  mover on the two boundary planes, pack both faces                       [main stream]
+//   EXCHANGE  face messages to / from the z-neighbours (periodic)                     [comm stream]
+//   INTERIOR  mover on the interior planes -- overlaps the exchange                   [main stream]
+//   GATHER_J  all-gather of the slabs' per-cell corner sums, J on every rank, fields  [comm, main]
+//   IMPORT    import interior planes; wait for the exchange; import the boundary planes,
+//             whose out-of-slab neighbours are columns of the received messages       [main stream]
+//
+// (PRE_DEPOSIT / PRE_GATHER_J: the projection pass of the interpolating mode, which needs J and the
+// field update before the mover.)
+
+enum SlabPhase { PH_PRE_DEPOSIT, PH_PRE_GATHER_J, PH_BOUNDARY, PH_EXCHANGE, PH_INTERIOR, PH_GATHER_J, PH_IMPORT, PH_COUNT };
+
+size_t faceBytes(const ipic_ctx* c, int64_t cap) {
+	const int nxy = c->g.nx * c->g.ny;
+	return (size_t)(alignUp((int64_t)(nxy + 1) * 4, 128) + cap * 64 + alignUp(cap, 128));
+}
+
+int64_t wantedMsgCap(const ipic_ctx* c) {
+	if (c->userMsgCap > 0) return c->userMsgCap;
+	return std::min<int64_t>(std::max<int64_t>(c->facePopulation / 16, 32768), (int64_t)1 << 26);
+}
+
+int allocExchange(ipic_ctx* c, int64_t cap) {
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaStreamSynchronize(c->commStream));
+	for (int i = 0; i < 2; i++) { cudaFree(c->sendMsg[i]); cudaFree(c->recvMsg[i]); c->sendMsg[i] = c->recvMsg[i] = nullptr; }
+	c->msgCap = (int)cap;
+	c->msgBytes = faceBytes(c, cap);
+	for (int i = 0; i < 2; i++) {
+		CK(cudaMalloc(&c->sendMsg[i], c->msgBytes));
+		CK(cudaMalloc(&c->recvMsg[i], c->msgBytes));
+		CK(cudaMemset(c->sendMsg[i], 0, c->msgBytes));
+		CK(cudaMemset(c->recvMsg[i], 0, c->msgBytes));
+	}
+	c->exchangeDirty = false;
+	return IPIC_OK;
+}
+
+// all ranks agree on max(wanted capacity); NCCL contexts must all enter this in the same ipic_step call
+int negotiateExchangeNccl(ipic_ctx* c) {
+	if (!c->exchangeDirty) return IPIC_OK;
+	CK(cudaSetDevice(c->device));
+	std::vector<int64_t> all((size_t)c->nranks, 0);
+	const int64_t mine = wantedMsgCap(c);
+	CK(cudaMemcpyAsync(c->dNegotiate + c->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, c->commStream));
+	int rc = comm_allgather(c->comm, c->dNegotiate + c->rank, c->dNegotiate, sizeof(int64_t), c->commStream, g_lastError);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(all.data(), c->dNegotiate, all.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, c->commStream));
+	CK(cudaStreamSynchronize(c->commStream));
+	int64_t cap = 0;
+	for (int64_t v : all) cap = std::max(cap, v);
+	return allocExchange(c, cap);
+}
+
+int negotiateExchangeGroup(ipic_group* grp) {
+	bool dirty = false;
+	int64_t cap = 0;
+	for (ipic_ctx* m : grp->members) { dirty = dirty || m->exchangeDirty; cap = std::max(cap, wantedMsgCap(m)); }
+	if (!dirty) return IPIC_OK;
+	for (ipic_ctx* m : grp->members) { int rc = allocExchange(m, cap); if (rc) return rc; }
+	return IPIC_OK;
+}
+
+ipic_ctx* neighbour(const ipic_ctx* c, int dir) {      // in-process group only
+	const int n = c->nranks;
+	return c->group->members[(size_t)((c->rank + dir + n) % n)];
+}
+
+// every rank ends up with the corner sums of all cells (slab r is the r-th contiguous piece of dCellJ)
+int allGatherCellJ(ipic_ctx* c) {
+	const size_t slabDoubles = (size_t)c->g.nx * c->g.ny * c->g.lz * 24;
+	CK(cudaStreamWaitEvent(c->commStream, c->evMoved, 0));
+	if (c->comm) {
+		int rc = comm_allgather(c->comm, c->dCellJ + (size_t)c->rank * slabDoubles, c->dCellJ, slabDoubles * sizeof(double), c->commStream, g_lastError);
+		if (rc) return rc;
+	} else {
+		for (ipic_ctx* m : c->group->members) {
+			if (m == c) continue;
+			CK(cudaStreamWaitEvent(c->commStream, m->evMoved, 0));
+			CK(cudaMemcpyPeerAsync(c->dCellJ + (size_t)m->rank * slabDoubles, c->device, m->dCellJ + (size_t)m->rank * slabDoubles, m->device,
+			                       slabDoubles * sizeof(double), c->commStream));
+		}
+	}
+	CK(cudaEventRecord(c->evJ, c->commStream));
+	CK(cudaStreamWaitEvent(c->stream, c->evJ, 0));
+	launch_gather_current(c->g, c->dCellJ, c->dJ, c->dStop, c->stream);
+	c->launches++;
+	return IPIC_OK;
+}
+
+// in-process group: nobody may still be copying my slab of dCellJ (previous step) when I overwrite it
+int waitPeersDoneWithCellJ(ipic_ctx* c) {
+	if (!c->group) return IPIC_OK;
+	for (ipic_ctx* m : c->group->members) if (m != c) CK(cudaStreamWaitEvent(c->stream, m->evJ, 0));
+	return IPIC_OK;
+}
+
+int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
+	CK(cudaSetDevice(c->device));
+	const int lz = c->g.lz;
+	const int out = c->cur ^ 1;
+	switch (phase) {
+	case PH_PRE_DEPOSIT:
+		if (!(f.project && f.interp)) break;
+		{ int rc = waitPeersDoneWithCellJ(c); if (rc) return rc; }
+		depositPass(c, f, 0, lz);
+		CK(cudaEventRecord(c->evMoved, c->stream));
+		break;
+	case PH_PRE_GATHER_J:
+		if (!(f.project && f.interp)) break;
+		{ int rc = allGatherCellJ(c); if (rc) return rc; }
+		break;
+	case PH_BOUNDARY: {
+		if (!f.fuseDeposit) fieldPhase(c, f);
+		if (f.fuseDeposit) { int rc = waitPeersDoneWithCellJ(c); if (rc) return rc; }
+		if (c->group && f.migrate) {
+			// the neighbours pulled last step's messages out of my send buffers on their comm streams
+			CK(cudaStreamWaitEvent(c->stream, neighbour(c, -1)->evRecv, 0));
+			CK(cudaStreamWaitEvent(c->stream, neighbour(c, +1)->evRecv, 0));
+		}
+		{
+			ProfSpan span(c, 0);
+			launch_move(moveArgs(c, f, 0, 1), c->stream);
+			c->launches++;
+			if (lz > 1) { launch_move(moveArgs(c, f, lz - 1, 1), c->stream); c->launches++; }
+		}
+		if (f.migrate) {
+			launch_face_pack(c->g, c->buf[out], c->dCellStart, c->dLeave, c->dTag, c->dFaceCnt, faceView(c, c->sendMsg[0]), faceView(c, c->sendMsg[1]),
+			                 c->dStop, stepIndex, c->stream);
+			c->launches += 3;
+			CK(cudaEventRecord(c->evPacked, c->stream));
+		}
+		break;
+	}
+	case PH_EXCHANGE:
+		if (!f.migrate) break;
+		CK(cudaStreamWaitEvent(c->commStream, c->evPacked, 0));
+		if (c->comm) {
+			int rc = comm_exchange(c->comm, c->sendMsg[1], c->recvMsg[0], c->sendMsg[0], c->recvMsg[1], c->msgBytes, c->commStream, g_lastError);
+			if (rc) return rc;
+		} else {
+			ipic_ctx* down = neighbour(c, -1);
+			ipic_ctx* up = neighbour(c, +1);
+			CK(cudaStreamWaitEvent(c->commStream, down->evPacked, 0));
+			CK(cudaStreamWaitEvent(c->commStream, up->evPacked, 0));
+			CK(cudaMemcpyPeerAsync(c->recvMsg[0], c->device, down->sendMsg[1], down->device, c->msgBytes, c->commStream));
+			CK(cudaMemcpyPeerAsync(c->recvMsg[1], c->device, up->sendMsg[0], up->device, c->msgBytes, c->commStream));
+		}
+		CK(cudaEventRecord(c->evRecv, c->commStream));
+		break;
+	case PH_INTERIOR:
+		if (lz > 2) {
+			ProfSpan span(c, 0);
+			launch_move(moveArgs(c, f, 1, lz - 2), c->stream);
+			c->launches++;
+		}
+		if (f.fuseDeposit) CK(cudaEventRecord(c->evMoved, c->stream));
+		break;
+	case PH_GATHER_J:
+		if (!f.fuseDeposit) break;
+		{ int rc = allGatherCellJ(c); if (rc) return rc; }
+		fieldPhase(c, f);
+		break;
+	case PH_IMPORT:
+		if (f.migrate) {
+			{
+				ProfSpan span(c, 1);
+				importPlanes(c, stepIndex, 1, lz - 2, false);
+			}
+			CK(cudaStreamWaitEvent(c->stream, c->evRecv, 0));
+			ProfSpan span(c, 1);
+			importPlanes(c, stepIndex, 0, 1, lz == 1);
+			if (lz > 1) importPlanes(c, stepIndex, lz - 1, 1, true);
+		} else {
+			CK(cudaMemcpyAsync(c->dCount, c->dStay, (size_t)c->g.ncellsLocal * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+		}
+		c->cur ^= 1;
+		CK(cudaGetLastError());
+		break;
+	default: break;
+	}
+	return IPIC_OK;
+}
+
+int enqueueStep(ipic_ctx* c, uint32_t flags, int stepIndex) {
+	const StepFlags f(flags);
+	if (c->nranks == 1) return enqueueStepSingle(c, f, stepIndex);
+	for (int ph = 0; ph < PH_COUNT; ph++) { int rc = slabPhase(c, ph, f, stepIndex); if (rc) return rc; }
+	return IPIC_OK;
+}
+
+int enqueueSteps(ipic_ctx* c, uint64_t first, uint64_t count, uint32_t flags) {
 	for (uint64_t s = first; s < first + count; s++) {
 		int rc = enqueueStep(c, flags, (int)std::min<uint64_t>(s, 0x7ffffff0u));
 		if (rc) return rc;
@@ -506,18 +797,124 @@ static int enqueueSteps(ipic_ctx* c, uint64_t first, uint64_t count, uint32_t fl
 	return IPIC_OK;
 }
 
+int stopError(ipic_ctx* c, const int* stop) {
+	if (stop[3] == 1) return fail(IPIC_ERR_CAPACITY, "rank %d: more than %d particles cross a slab face in step %d: raise ipic_set_exchange_capacity", c->rank, c->msgCap, stop[1]);
+	if (stop[3] == 2) return fail(IPIC_ERR_CAPACITY, "rank %d: unusable face message received in step %d (the sending rank ran out of message space: raise ipic_set_exchange_capacity)", c->rank, stop[1]);
+	return fail(IPIC_ERR_CAPACITY, "rank %d: cell segment overflow in a multi-GPU run (step %d): raise the head-room with ipic_set_headroom", c->rank, stop[1]);
+}
+
+// Did the slab step whose PH_IMPORT was enqueued last complete without overflowing a cell segment?  If it
+// did overflow: the generation being written still holds every stayer and every outbox, and the received
+// face messages are untouched, so this rank re-layouts on its own and redoes that import; nothing of the NEXT step has left
+// this GPU yet (see runSlabSteps), so the other ranks never see the hiccup.
+int confirmSlabStep(ipic_ctx* c, bool* recovered) {
+	*recovered = false;
+	CK(cudaSetDevice(c->device));
+	CK(cudaEventSynchronize(c->evStepDone));
+	if (!c->hStop[0]) return IPIC_OK;
+	if (c->hStop[3]) return stopError(c, c->hStop);
+	const int failed = c->hStop[1];
+	CK(cudaStreamSynchronize(c->stream));                    // drain the (skipped) launches queued behind the failure
+	int rc = relayoutAfterOverflow(c, c->cur, failed);
+	if (rc) return rc;
+	c->relayouts++;
+	*recovered = true;
+	return IPIC_OK;
+}
+
+bool phaseCommunicates(int ph, const StepFlags& f) {
+	switch (ph) {
+	case PH_PRE_GATHER_J: return f.project && f.interp;
+	case PH_EXCHANGE: return f.migrate;
+	case PH_GATHER_J: return f.fuseDeposit;
+	default: return false;
+	}
+}
+
+// Steps of slab contexts (one NCCL rank, or all members of an in-process group).  The host runs at most
+// one step ahead of the device: before the first communication of step s is enqueued, step s-1 is
+// confirmed (and repaired if a cell segment overflowed).  The launches of step s queued before that
+// point (boundary movers + pack, or the projection pass) keep the GPU busy meanwhile.
+int runSlabSteps(ipic_ctx** ctxs, int n, uint64_t numSteps, uint32_t flags, double* tFirst, double* tRest) {
+	const StepFlags f(flags);
+	std::vector<cudaEvent_t> ev((size_t)n * 3);
+	for (int r = 0; r < n; r++) {
+		CK(cudaSetDevice(ctxs[r]->device));
+		for (int k = 0; k < 3; k++) CK(cudaEventCreate(&ev[(size_t)r * 3 + k]));
+		CK(cudaEventRecord(ev[(size_t)r * 3], ctxs[r]->stream));
+	}
+	auto confirmAll = [&](int stepIndex, int uptoPhase) -> int {
+		for (int r = 0; r < n; r++) {
+			bool recovered = false;
+			int rc = confirmSlabStep(ctxs[r], &recovered);
+			if (rc) return rc;
+			// the launches of the current step that were queued behind the failure did nothing: queue them again
+			if (recovered) for (int q = 0; q < uptoPhase; q++) { rc = slabPhase(ctxs[r], q, f, stepIndex); if (rc) return rc; }
+		}
+		return IPIC_OK;
+	};
+	for (uint64_t s = 0; s < numSteps; s++) {
+		const int stepIndex = (int)std::min<uint64_t>(s, 0x7ffffff0u);
+		bool confirmed = s == 0;
+		for (int ph = 0; ph < PH_COUNT; ph++) {
+			if (!confirmed && (phaseCommunicates(ph, f) || ph == PH_IMPORT)) {
+				int rc = confirmAll(stepIndex, ph);
+				if (rc) return rc;
+				confirmed = true;
+			}
+			for (int r = 0; r < n; r++) { int rc = slabPhase(ctxs[r], ph, f, stepIndex); if (rc) return rc; }
+		}
+		for (int r = 0; r < n; r++) {
+			ipic_ctx* c = ctxs[r];
+			CK(cudaSetDevice(c->device));
+			if (s == 0) CK(cudaEventRecord(ev[(size_t)r * 3 + 1], c->stream));
+			CK(cudaMemcpyAsync(c->hStop, c->dStop, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+			CK(cudaEventRecord(c->evStepDone, c->stream));
+		}
+	}
+	{ int rc = confirmAll(0, 0); if (rc) return rc; }
+	float msFirst = 0, msRest = 0;
+	for (int r = 0; r < n; r++) {
+		ipic_ctx* c = ctxs[r];
+		CK(cudaSetDevice(c->device));
+		CK(cudaEventRecord(ev[(size_t)r * 3 + 2], c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		CK(cudaStreamSynchronize(c->commStream));
+		float a = 0, b = 0;
+		CK(cudaEventElapsedTime(&a, ev[(size_t)r * 3], ev[(size_t)r * 3 + 1]));
+		CK(cudaEventElapsedTime(&b, ev[(size_t)r * 3 + 1], ev[(size_t)r * 3 + 2]));
+		msFirst = std::max(msFirst, a); msRest = std::max(msRest, b);
+		if (c->profiling) { int rc = drainProfile(c); if (rc) return rc; }
+		for (int k = 0; k < 3; k++) cudaEventDestroy(ev[(size_t)r * 3 + k]);
+	}
+	if (tFirst) *tFirst = msFirst / 1000.0;
+	if (tRest) *tRest = msRest / 1000.0;
+	return IPIC_OK;
+}
+
+} // namespace
+
 static int checkStepArgs(ipic_ctx* c, uint32_t flags) {
 	if (!c) return fail(IPIC_ERR_ARG, "null context");
 	if (!c->haveCells) return fail(IPIC_ERR_ARG, "ipic_upload_cells has not been called");
 	if ((flags & IPIC_SOLVER_FORWARD) && (flags & IPIC_SOLVER_LEAPFROG)) return fail(IPIC_ERR_ARG, "choose one field solver");
 	if ((flags & IPIC_UPDATE_BOUNDARIES) && !(c->g.nx == c->g.ny && c->g.ny == c->g.nz)) return fail(IPIC_ERR_ARG, "updateFieldsOnBoundaries assumes a cubic universe (reference field.h:422)");
-	if (c->nranks > 1 && !c->comm) return fail(IPIC_ERR_COMM, "slab context %d/%d has no communicator (ipic_comm_init)", c->rank, c->nranks);
+	if (c->nranks > 1 && !c->comm && !c->group) return fail(IPIC_ERR_COMM, "slab context %d/%d has no communicator (ipic_comm_init / ipic_group_create)", c->rank, c->nranks);
+	return IPIC_OK;
+}
+
+static int checkSoloStep(ipic_ctx* c, uint32_t flags) {
+	int rc = checkStepArgs(c, flags);
+	if (rc) return rc;
+	if (c->group) return fail(IPIC_ERR_ARG, "context %d/%d belongs to an in-process group: step it with ipic_group_step", c->rank, c->nranks);
+	if (c->nranks > 1) return negotiateExchangeNccl(c);
 	return IPIC_OK;
 }
 
 int ipic_step_async(ipic_ctx* c, uint64_t numSteps, uint32_t flags) {
-	int rc = checkStepArgs(c, flags);
+	int rc = checkSoloStep(c, flags);
 	if (rc) return rc;
+	if (c->nranks > 1) return fail(IPIC_ERR_ARG, "ipic_step_async is for single-GPU contexts: slab steps confirm every step on the host (ipic_step)");
 	CK(cudaSetDevice(c->device));
 	return enqueueSteps(c, 0, numSteps, flags);
 }
@@ -532,9 +929,10 @@ int ipic_sync(ipic_ctx* c) {
 int ipic_step(ipic_ctx* c, uint64_t numSteps, uint32_t flags, double* tFirst, double* tRest) {
 	if (tFirst) *tFirst = 0;
 	if (tRest) *tRest = 0;
-	{ int rc = checkStepArgs(c, flags); if (rc) return rc; }
+	{ int rc = checkSoloStep(c, flags); if (rc) return rc; }
 	if (numSteps == 0) return IPIC_OK;
 	CK(cudaSetDevice(c->device));
+	if (c->nranks > 1) return runSlabSteps(&c, 1, numSteps, flags, tFirst, tRest);
 	cudaEvent_t ev[3];
 	for (auto& e : ev) CK(cudaEventCreate(&e));
 	uint64_t done = 0;
@@ -556,15 +954,15 @@ int ipic_step(ipic_ctx* c, uint64_t numSteps, uint32_t flags, double* tFirst, do
 		CK(cudaEventElapsedTime(&b, ev[1], ev[2]));
 		if (done == 0) { msFirst += a; msRest += b; } else { msRest += a + b; }
 		if (c->profiling) { rc = drainProfile(c); if (rc) return rc; }
-		int stop[3];
+		int stop[4];
 		CK(cudaMemcpy(stop, c->dStop, sizeof stop, cudaMemcpyDeviceToHost));
 		if (!stop[0]) { done = numSteps; break; }
 		// import of step `stop[1]` of this batch overflowed; later steps were skipped on the device
 		const int failed = stop[1];
 		const int outGen = genAtStart ^ ((failed + 1) & 1);
-		if (c->nranks > 1) return fail(IPIC_ERR_CAPACITY, "cell segment overflow in a multi-GPU run (step %d): raise the head-room with ipic_set_headroom", failed);
 		rc = relayoutAfterOverflow(c, outGen, failed);
 		if (rc) return rc;
+		c->relayouts++;
 		c->cur = outGen;
 		done += (uint64_t)failed + 1;
 	}
@@ -572,6 +970,46 @@ int ipic_step(ipic_ctx* c, uint64_t numSteps, uint32_t flags, double* tFirst, do
 	if (tFirst) *tFirst = msFirst / 1000.0;
 	if (tRest) *tRest = msRest / 1000.0;
 	return IPIC_OK;
+}
+
+int ipic_group_create(const ipic_props* props, const int* devices, int ndev, ipic_ctx** out) {
+	if (!props || !devices || !out || ndev < 1) return fail(IPIC_ERR_ARG, "bad group arguments");
+	auto grp = std::make_shared<ipic_group>();
+	for (int r = 0; r < ndev; r++) {
+		ipic_ctx* c = nullptr;
+		int rc = ipic_create_slab(props, devices[r], r, ndev, &c);
+		if (rc) { for (ipic_ctx* m : grp->members) { m->group.reset(); ipic_destroy(m); } return rc; }
+		grp->members.push_back(c);
+	}
+	for (int r = 0; r < ndev; r++) {
+		if (ndev > 1) grp->members[(size_t)r]->group = grp;
+		out[r] = grp->members[(size_t)r];
+	}
+	// direct peer copies between distinct devices where the hardware allows it (cudaMemcpyPeerAsync works either way)
+	for (int a = 0; a < ndev; a++) for (int b = 0; b < ndev; b++) {
+		if (devices[a] == devices[b]) continue;
+		int can = 0;
+		if (cudaDeviceCanAccessPeer(&can, devices[a], devices[b]) == cudaSuccess && can) { cudaSetDevice(devices[a]); cudaDeviceEnablePeerAccess(devices[b], 0); }
+	}
+	cudaGetLastError();      // "peer access already enabled" is not an error
+	return IPIC_OK;
+}
+
+int ipic_group_step(ipic_ctx** ctxs, int n, uint64_t numSteps, uint32_t flags, double* tFirst, double* tRest) {
+	if (tFirst) *tFirst = 0;
+	if (tRest) *tRest = 0;
+	if (!ctxs || n < 1 || !ctxs[0]) return fail(IPIC_ERR_ARG, "bad group arguments");
+	if (n == 1) return ipic_step(ctxs[0], numSteps, flags, tFirst, tRest);
+	ipic_group* grp = ctxs[0]->group.get();
+	if (!grp || (int)grp->members.size() != n) return fail(IPIC_ERR_ARG, "the contexts are not the %d members of one group", n);
+	for (int r = 0; r < n; r++) {
+		if (ctxs[r] != grp->members[(size_t)r] || !ctxs[r]) return fail(IPIC_ERR_ARG, "the contexts are not the members of one group in rank order");
+		int rc = checkStepArgs(ctxs[r], flags);
+		if (rc) return rc;
+	}
+	if (numSteps == 0) return IPIC_OK;
+	{ int rc = negotiateExchangeGroup(grp); if (rc) return rc; }
+	return runSlabSteps(ctxs, n, numSteps, flags, tFirst, tRest);
 }
 
 int ipic_count_misplaced(ipic_ctx* c, uint64_t* misplaced) {
@@ -622,6 +1060,12 @@ int ipic_profile_get(ipic_ctx* c, double* moverMs, double* importMs, uint64_t* l
 	if (moverMs) *moverMs = c->moverMs;
 	if (importMs) *importMs = c->importMs;
 	if (launches) *launches = c->launches;
+	return IPIC_OK;
+}
+
+int ipic_relayout_count(ipic_ctx* c, uint64_t* count) {
+	if (!c || !count) return fail(IPIC_ERR_ARG, "null argument");
+	*count = c->relayouts;
 	return IPIC_OK;
 }
 

@@ -88,7 +88,7 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	const int xy = blockIdx.x / zCount;
 	const int zl = zBegin + (blockIdx.x - xy * zCount);          // owned z-plane within the slab
 	const int cx = xy / g.ny, cy = xy - cx * g.ny, cz = g.z0 + zl;
-	const int cell = xy * g.lzs + zl + g.ghost;
+	const int cell = xy * g.lz + zl;
 
 	extern __shared__ __align__(128) double sTile[];             // stages x TILE_DOUBLES
 	__shared__ uint64_t sFull[kMaxStages];
@@ -294,7 +294,7 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 		phase ^= 1;
 	}
 	if (PUSH && tid == 0) { countOut[cell] = kept; nLeave[cell] = left; }
-	if (DEPOSIT && tid < 24) cellJ[(((int64_t)cx * g.ny + cy) * g.nz + cz) * 24 + tid] = sJ[tid];      // indexed by GLOBAL cell id
+	if (DEPOSIT && tid < 24) cellJ[cellj_index(g, cx, cy, cz) + tid] = sJ[tid];      // GLOBAL cell id, z-major: a slab is contiguous
 }
 
 // ---- import: append the 26 incoming outboxes in canonical order (reference cell.h:1195-1310) ------
@@ -305,22 +305,43 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 // neighbour has more than 32 leavers (the common case) all 26 tag rows are fetched at once, the hits are
 // turned into 26 ballots, and every arrival is copied by its own lane: three dependent memory round
 // trips per cell instead of 2 x 26.
+//
+// SLAB: the universe is split into z-slabs; a neighbour below the slab's first plane / above its last
+// one lives on another GPU, and its outbox is the matching column of the face message received from
+// that GPU (k_face_copy: same entries, same order, AoS payload).
 
 constexpr int kImportBlock = 256;
 constexpr int kImportWarps = kImportBlock / 32;
 
-__device__ __forceinline__ void copy_particle(const double* __restrict__ s, double* __restrict__ t) {
-	double v[kFields];
-	#pragma unroll
-	for (int f = 0; f < kFields; f++) v[f] = s[f * kFieldStride];
-	#pragma unroll
-	for (int f = 0; f < kFields; f++) t[f * kFieldStride] = v[f];
-}
+// outbox entry j of a source: local outboxes grow backwards from the end of the cell's segment,
+// message columns forwards from the column's first entry
+struct ImportSource {
+	const unsigned char* tags;
+	const double* data;
+	bool remote;
+	__device__ __forceinline__ unsigned char tagOf(int64_t base, int j) const { return remote ? tags[base + j] : tags[base - j]; }
+	__device__ __forceinline__ void copyTo(int64_t base, int j, double* __restrict__ t) const {
+		double v[kFields];
+		if (remote) {
+			const double2* s = reinterpret_cast<const double2*>(data + (base + j) * kFields);
+			#pragma unroll
+			for (int f = 0; f < kFields; f += 2) { const double2 x = s[f >> 1]; v[f] = x.x; v[f + 1] = x.y; }
+		} else {
+			const double* s = data + slot_index(base - j);
+			#pragma unroll
+			for (int f = 0; f < kFields; f++) v[f] = s[f * kFieldStride];
+		}
+		#pragma unroll
+		for (int f = 0; f < kFields; f++) t[f * kFieldStride] = v[f];
+	}
+};
 
+template<bool SLAB>
 __global__ void __launch_bounds__(kImportBlock)
 k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__ srcStart, const int* __restrict__ srcLeave,
          const unsigned char* __restrict__ tag, const ParticleArrays dst, const int64_t* __restrict__ dstStart,
-         const int* __restrict__ stay, int* __restrict__ dstCount, int reserveOwnOutbox, int* __restrict__ stopFlag, int stepIndex, int zBegin, int zCount) {
+         const int* __restrict__ stay, int* __restrict__ dstCount, int reserveOwnOutbox, int* __restrict__ stopFlag, int stepIndex, int zBegin, int zCount,
+         const FaceMsg fromDown, const FaceMsg fromUp) {
 
 	if (*(volatile int*)stopFlag) return;
 	const int lane = threadIdx.x & 31;
@@ -329,24 +350,47 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 	const int xy = task / zCount;
 	const int zl = zBegin + (task - xy * zCount);
 	const int cx = xy / g.ny, cy = xy - cx * g.ny;
-	const int cell = xy * g.lzs + zl + g.ghost;
+	const int cell = xy * g.lz + zl;
 
 	const int64_t dbase = dstStart[cell];
 	const int dcap = (int)(dstStart[cell + 1] - dbase);
 	const int room = dcap - (reserveOwnOutbox ? srcLeave[cell] : 0);
 	int w = stay[cell];
 
-	// lane d: its neighbour's outbox
+	// source of direction d (uniform over the warp): the local outbox, or a column of a face message
+	auto sourceOf = [&](int d) {
+		ImportSource s;
+		const int c = d % 3;
+		s.remote = SLAB && ((c == 0 && zl == 0) || (c == 2 && zl == g.lz - 1));
+		if (s.remote) { const FaceMsg& m = c == 0 ? fromDown : fromUp; s.tags = m.tags; s.data = m.particles; }
+		else { s.tags = tag; s.data = src.d; }
+		return s;
+	};
+
+	// lane d: its neighbour's outbox (number of entries, index base)
 	int myLeave = 0;
-	int64_t mySend = 0;
+	int64_t myBase = 0;
+	bool corrupt = false;
 	if (lane < 27 && lane != 13) {
 		const int a = lane / 9, b = (lane / 3) % 3, c = lane % 3;
 		const int sx = (cx + a - 1 + g.nx) % g.nx, sy = (cy + b - 1 + g.ny) % g.ny;
-		int szl = zl + c - 1;                         // local z; ghost planes hold the neighbours' rows
-		if (!g.ghost) szl = (szl + g.lz) % g.lz;
-		const int scell = (sx * g.ny + sy) * g.lzs + szl + g.ghost;
-		myLeave = srcLeave[scell];
-		mySend = srcStart[scell + 1] - 1;             // outbox entry j lives at slot mySend - j
+		if (SLAB && ((c == 0 && zl == 0) || (c == 2 && zl == g.lz - 1))) {
+			const FaceMsg& m = c == 0 ? fromDown : fromUp;
+			const int first = m.offsets[sx * g.ny + sy];
+			myLeave = m.offsets[sx * g.ny + sy + 1] - first;
+			myBase = first;
+			if (first < 0 || myLeave < 0 || first + myLeave > m.cap) { corrupt = true; myLeave = 0; }
+		} else {
+			const int szl = (zl + c - 1 + g.lz) % g.lz;
+			const int scell = (sx * g.ny + sy) * g.lz + szl;
+			myLeave = srcLeave[scell];
+			myBase = srcStart[scell + 1] - 1;             // outbox entry j lives at slot myBase - j
+		}
+	}
+	if (SLAB && __any_sync(0xffffffffu, corrupt)) {
+		// the sender ran out of message space (it reports that itself) or the message is damaged
+		if (lane == 0) { atomicMin(stopFlag + 1, stepIndex); atomicExch(stopFlag + 3, 2); atomicExch(stopFlag, 1); }
+		return;
 	}
 	const int maxLeave = __reduce_max_sync(0xffffffffu, myLeave);
 	if (maxLeave == 0) {
@@ -362,8 +406,8 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 			for (int d = 0; d < 27; d++) {
 				if (d == 13) continue;
 				const int nl = __shfl_sync(0xffffffffu, myLeave, d);
-				const int64_t send = __shfl_sync(0xffffffffu, mySend, d);
-				t[d] = lane < nl ? tag[send - lane] : kTagNone;
+				const int64_t base = __shfl_sync(0xffffffffu, myBase, d);
+				t[d] = lane < nl ? sourceOf(d).tagOf(base, lane) : kTagNone;
 			}
 			#pragma unroll
 			for (int d = 0; d < 27; d++) {
@@ -384,9 +428,8 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 				if (i >= pre && i < pre + cnt) { dsel = d; jsel = (int)__fns(mask[d], 0, i - pre + 1); }
 				pre += cnt;
 			}
-			const int64_t send = __shfl_sync(0xffffffffu, mySend, dsel);
-			if (i < total && w + i < room)
-				copy_particle(src.d + slot_index(send - jsel), dst.d + slot_index(dbase + w + i));
+			const int64_t base = __shfl_sync(0xffffffffu, myBase, dsel);
+			if (i < total && w + i < room) sourceOf(dsel).copyTo(base, jsel, dst.d + slot_index(dbase + w + i));
 		}
 		w += total;
 	} else {
@@ -395,15 +438,16 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 			if (d == 13) continue;
 			const int nl = __shfl_sync(0xffffffffu, myLeave, d);
 			if (nl == 0) continue;
-			const int64_t send = __shfl_sync(0xffffffffu, mySend, d);
+			const int64_t base = __shfl_sync(0xffffffffu, myBase, d);
+			const ImportSource s = sourceOf(d);
 			const unsigned want = (unsigned)((2 - d / 9) * 9 + (2 - (d / 3) % 3) * 3 + (2 - d % 3));
 			for (int j0 = 0; j0 < nl; j0 += 32) {
 				const int j = j0 + lane;
-				const bool hit = j < nl && tag[send - j] == want;
+				const bool hit = j < nl && s.tagOf(base, j) == want;
 				const unsigned m = __ballot_sync(0xffffffffu, hit);
 				if (hit) {
 					const int o = w + __popc(m & ((1u << lane) - 1u));
-					if (o < room) copy_particle(src.d + slot_index(send - j), dst.d + slot_index(dbase + o));
+					if (o < room) s.copyTo(base, j, dst.d + slot_index(dbase + o));
 				}
 				w += __popc(m);
 			}
@@ -419,6 +463,117 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 // failing step still gets its import attempt recorded in dstCount == required size)
 __global__ void k_commit_flag(int* stopFlag) {
 	if (stopFlag[2]) stopFlag[0] = 1;
+}
+
+
+// ---- z-slab faces: pack the leavers that cross the slab boundary, unpack into ghost cells ----------
+//
+// Face 0 = the slab's lowest owned z-plane, leavers with direction k = 0 (to the neighbour below);
+// face 1 = the highest owned plane, k = 2 (to the neighbour above).  A face message is
+//   offsets[nx*ny + 1]  exclusive prefix of the entries per (x,y) column, offsets[nx*ny] = total
+//   particles[cap][8]   AoS, columns in (x*ny + y) order, each column in outbox order
+//   tags[cap]           full direction code of every entry
+// i.e. for the receiver's import kernel a column is exactly the outbox it would have found in the
+// neighbour's cell (the reference's transfer buffers of that cell, transfer_buffer.h:15-95), restricted
+// to the entries that can concern it: arrival order stays canonical across slab boundaries.
+
+constexpr int kFaceBlock = 256;
+constexpr int kFaceWarps = kFaceBlock / 32;
+
+__global__ void __launch_bounds__(kFaceBlock)
+k_face_count(const Geometry g, const int64_t* __restrict__ cellStart, const int* __restrict__ nLeave,
+             const unsigned char* __restrict__ tag, int* __restrict__ faceCnt, const int* __restrict__ stopFlag) {
+	const int lane = threadIdx.x & 31;
+	const int nxy = g.nx * g.ny;
+	const int task = blockIdx.x * kFaceWarps + (threadIdx.x >> 5);
+	if (task >= 2 * nxy) return;
+	int cnt = 0;
+	if (!*stopFlag) {
+		const int f = task / nxy, xy = task - f * nxy;
+		const int cell = xy * g.lz + (f ? g.lz - 1 : 0);
+		const int nl = nLeave[cell];
+		const int64_t send = cellStart[cell + 1] - 1;
+		const unsigned want = f ? 2u : 0u;
+		for (int j0 = 0; j0 < nl; j0 += 32) {
+			const int j = j0 + lane;
+			const bool hit = j < nl && (tag[send - j] % 3u) == want;
+			cnt += __popc(__ballot_sync(0xffffffffu, hit));
+		}
+	}
+	if (lane == 0) faceCnt[task] = cnt;
+}
+
+// one CTA of 1024 threads per face: exclusive scan of the column counts into the message header
+__global__ void __launch_bounds__(1024)
+k_face_scan(const Geometry g, const int* __restrict__ faceCnt, FaceMsg m0, FaceMsg m1, int* __restrict__ stopFlag, int stepIndex) {
+	__shared__ int sWarp[32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int nxy = g.nx * g.ny;
+	const FaceMsg m = blockIdx.x ? m1 : m0;
+	const int* cnt = faceCnt + blockIdx.x * nxy;
+	int carry = 0;
+	for (int base = 0; base < nxy; base += 1024) {
+		const int i = base + tid;
+		const int v = i < nxy ? cnt[i] : 0;
+		int incl = v;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+		if (lane == 31) sWarp[warp] = incl;
+		__syncthreads();
+		if (warp == 0) {
+			int w = sWarp[lane];
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += t; }
+			sWarp[lane] = w;
+		}
+		__syncthreads();
+		if (i < nxy) m.offsets[i] = carry + (warp ? sWarp[warp - 1] : 0) + incl - v;
+		carry += sWarp[31];
+		__syncthreads();
+	}
+	if (tid == 0) {
+		m.offsets[nxy] = carry;
+		if (carry > m.cap) { atomicMin(stopFlag + 1, stepIndex); atomicExch(stopFlag + 3, 1); atomicExch(stopFlag, 1); }
+	}
+}
+
+__global__ void __launch_bounds__(kFaceBlock)
+k_face_copy(const Geometry g, const ParticleArrays src, const int64_t* __restrict__ cellStart, const int* __restrict__ nLeave,
+            const unsigned char* __restrict__ tag, FaceMsg m0, FaceMsg m1) {
+	const int lane = threadIdx.x & 31;
+	const int nxy = g.nx * g.ny;
+	const int task = blockIdx.x * kFaceWarps + (threadIdx.x >> 5);
+	if (task >= 2 * nxy) return;
+	const int f = task / nxy, xy = task - f * nxy;
+	const FaceMsg m = f ? m1 : m0;
+	const int first = m.offsets[xy], total = m.offsets[xy + 1] - first;
+	if (total <= 0) return;
+	const int cell = xy * g.lz + (f ? g.lz - 1 : 0);
+	const int nl = nLeave[cell];
+	const int64_t send = cellStart[cell + 1] - 1;
+	const unsigned want = f ? 2u : 0u;
+	int w = 0;
+	for (int j0 = 0; j0 < nl; j0 += 32) {
+		const int j = j0 + lane;
+		unsigned char t = kTagNone;
+		if (j < nl) t = tag[send - j];
+		const bool hit = j < nl && (t % 3u) == want;
+		const unsigned mask = __ballot_sync(0xffffffffu, hit);
+		if (hit) {
+			const int o = first + w + __popc(mask & ((1u << lane) - 1u));
+			if (o < m.cap) {
+				const double* s = src.d + slot_index(send - j);
+				double v[kFields];
+				#pragma unroll
+				for (int k = 0; k < kFields; k++) v[k] = s[k * kFieldStride];
+				double2* d = reinterpret_cast<double2*>(m.particles + (int64_t)o * kFields);
+				#pragma unroll
+				for (int k = 0; k < kFields; k += 2) d[k >> 1] = make_double2(v[k], v[k + 1]);
+				m.tags[o] = t;
+			}
+		}
+		w += __popc(mask);
+	}
 }
 
 // ---- node-centric gather of the per-cell corner sums (reference cell.h:787-824) -------------------
@@ -437,8 +592,7 @@ __global__ void k_gather_current(const Geometry g, const double* __restrict__ ce
 		ux = ux < 0 ? g.nx - 1 : (ux >= g.nx ? 0 : ux);
 		uy = uy < 0 ? g.ny - 1 : (uy >= g.ny ? 0 : uy);
 		uz = uz < 0 ? g.nz - 1 : (uz >= g.nz ? 0 : uz);
-		const int64_t cell = ((int64_t)ux * g.ny + uy) * g.nz + uz;       // cellJ is indexed by GLOBAL cell id
-		Js += cellJ[cell * 24 + (((-i) * 2 + (-j)) * 2 + (-k)) * 3 + comp];
+		Js += cellJ[cellj_index(g, ux, uy, uz) + (((-i) * 2 + (-j)) * 2 + (-k)) * 3 + comp];   // cellJ is indexed by GLOBAL cell id
 	}
 	J[t] = (Js / g.vol) / 8.0;
 }
@@ -450,7 +604,7 @@ __global__ void k_count_misplaced(const Geometry g, const ParticleArrays p, cons
 	const int xyz = blockIdx.x;
 	const int zl = xyz % g.lz, xy = xyz / g.lz;
 	const int cx = xy / g.ny, cy = xy - cx * g.ny, cz = g.z0 + zl;
-	const int cell = xy * g.lzs + zl + g.ghost;
+	const int cell = xy * g.lz + zl;
 	const double c0 = g.origin[0] + (double)cx * g.w[0] + g.w[0] / 2.0;
 	const double c1 = g.origin[1] + (double)cy * g.w[1] + g.w[1] / 2.0;
 	const double c2 = g.origin[2] + (double)cz * g.w[2] + g.w[2] / 2.0;
@@ -472,7 +626,7 @@ __global__ void k_scatter_aos(const Geometry g, const double* __restrict__ aos, 
                               const ParticleArrays p, const int64_t* __restrict__ cellStart) {
 	const int oc = blockIdx.x;
 	const int zl = oc % g.lz, xy = oc / g.lz;
-	const int cell = xy * g.lzs + zl + g.ghost;
+	const int cell = xy * g.lz + zl;
 	const int64_t a0 = aosStart[oc], n = aosStart[oc + 1] - a0, base = cellStart[cell];
 	for (int64_t e = threadIdx.x; e < n * 8; e += blockDim.x) p.d[slot_index(base + (e >> 3)) + (e & 7) * kFieldStride] = aos[a0 * 8 + e];
 }
@@ -481,7 +635,7 @@ __global__ void k_gather_aos(const Geometry g, double* __restrict__ aos, const i
                              const ParticleArrays p, const int64_t* __restrict__ cellStart) {
 	const int oc = blockIdx.x;
 	const int zl = oc % g.lz, xy = oc / g.lz;
-	const int cell = xy * g.lzs + zl + g.ghost;
+	const int cell = xy * g.lz + zl;
 	const int64_t a0 = aosStart[oc], n = aosStart[oc + 1] - a0, base = cellStart[cell];
 	for (int64_t e = threadIdx.x; e < n * 8; e += blockDim.x) aos[a0 * 8 + e] = p.d[slot_index(base + (e >> 3)) + (e & 7) * kFieldStride];
 }
@@ -491,7 +645,7 @@ __global__ void k_copy_heads(const Geometry g, const ParticleArrays src, const i
                              const ParticleArrays dst, const int64_t* __restrict__ dstStart, const int* __restrict__ count) {
 	const int oc = blockIdx.x;
 	const int zl = oc % g.lz, xy = oc / g.lz;
-	const int cell = xy * g.lzs + zl + g.ghost;
+	const int cell = xy * g.lz + zl;
 	const int64_t s0 = srcStart[cell], d0 = dstStart[cell];
 	const int n = count[cell];
 	// both segment starts are multiples of 32 slots: whole AoSoA blocks line up, copy them double by double
@@ -572,12 +726,24 @@ void launch_move(const MoveArgs& a, cudaStream_t st) {
 	else launch_move_i<1>(a, st);
 }
 
-void launch_import(const ImportArgs& a, cudaStream_t st) {
+void launch_import(const ImportArgs& a, bool commit, cudaStream_t st) {
 	const int tasks = a.g.nx * a.g.ny * a.zCount;
 	if (tasks == 0) return;
-	k_import<<<(tasks + kImportWarps - 1) / kImportWarps, kImportBlock, 0, st>>>(a.g, a.src, a.srcStart, a.srcLeave, a.tag, a.dst, a.dstStart, a.stay, a.dstCount,
-	                                                         a.reserveOwnOutbox, a.stopFlag, a.stepIndex, a.zBegin, a.zCount);
-	k_commit_flag<<<1, 1, 0, st>>>(a.stopFlag);
+	const int grid = (tasks + kImportWarps - 1) / kImportWarps;
+	if (a.slab) k_import<true><<<grid, kImportBlock, 0, st>>>(a.g, a.src, a.srcStart, a.srcLeave, a.tag, a.dst, a.dstStart, a.stay, a.dstCount,
+	                                                        a.reserveOwnOutbox, a.stopFlag, a.stepIndex, a.zBegin, a.zCount, a.fromDown, a.fromUp);
+	else k_import<false><<<grid, kImportBlock, 0, st>>>(a.g, a.src, a.srcStart, a.srcLeave, a.tag, a.dst, a.dstStart, a.stay, a.dstCount,
+	                                                    a.reserveOwnOutbox, a.stopFlag, a.stepIndex, a.zBegin, a.zCount, FaceMsg{}, FaceMsg{});
+	if (commit) k_commit_flag<<<1, 1, 0, st>>>(a.stopFlag);
+}
+
+void launch_face_pack(const Geometry& g, const ParticleArrays& src, const int64_t* cellStart, const int* nLeave, const unsigned char* tag,
+                      int* faceCnt, const FaceMsg& down, const FaceMsg& up, int* stopFlag, int stepIndex, cudaStream_t st) {
+	const int tasks = 2 * g.nx * g.ny;
+	const int grid = (tasks + kFaceWarps - 1) / kFaceWarps;
+	k_face_count<<<grid, kFaceBlock, 0, st>>>(g, cellStart, nLeave, tag, faceCnt, stopFlag);
+	k_face_scan<<<2, 1024, 0, st>>>(g, faceCnt, down, up, stopFlag, stepIndex);
+	k_face_copy<<<grid, kFaceBlock, 0, st>>>(g, src, cellStart, nLeave, tag, down, up);
 }
 
 void launch_gather_current(const Geometry& g, const double* cellJ, double* J, const int* stopFlag, cudaStream_t st) {

@@ -82,13 +82,30 @@ IPIC_API int  ipic_create_slab(const ipic_props* props, int device, int rank, in
 IPIC_API int  ipic_destroy(ipic_ctx* ctx);
 
 /* Head-room of a cell's segment in HBM: room for n*(1+slack) particles, at least n+min_pad.  When an
- * import still overflows a segment, single-GPU contexts re-layout transparently. */
+ * import still overflows a segment the context re-layouts transparently (see ipic_relayout_count). */
 IPIC_API int  ipic_set_headroom(ipic_ctx* ctx, double slack, int64_t min_pad);
+/* Number of times a cell segment overflowed and the context re-laid out its particle storage (the step
+ * that overflowed is redone; results are unaffected).  Slab contexts repair themselves the same way:
+ * ipic_step confirms every slab step on the host before the next step's exchange is enqueued. */
+IPIC_API int  ipic_relayout_count(ipic_ctx* ctx, uint64_t* count);
 
 /* Multi-GPU wiring (z-slab neighbours, NCCL send/recv).  unique_id is NCCL's 128-byte id,
  * produced on rank 0 by ipic_comm_unique_id and distributed by the caller. */
 IPIC_API int  ipic_comm_unique_id(void* unique_id_128);
 IPIC_API int  ipic_comm_init(ipic_ctx* ctx, const void* unique_id_128);
+
+/* Capacity, in particles, of one face message of the z-slab exchange (fixed-size NCCL send/recv per
+ * face and step).  0 = automatic: 1/16 of the fuller boundary plane's population, at least 32768; the
+ * ranks agree on the maximum at the next step.  Must be called on all ranks alike. */
+IPIC_API int  ipic_set_exchange_capacity(ipic_ctx* ctx, int64_t particles);
+
+/* Single-process multi-GPU: ndev slab contexts (rank r on devices[r]; devices may repeat) that exchange
+ * by peer copies instead of NCCL.  This is what a single-process caller such as the reference's
+ * simulateSteps uses to drive all GPUs of a box.  Upload / download each member with the functions
+ * below (rank r owns the z-planes [r*nz/ndev, (r+1)*nz/ndev)); step all members together with
+ * ipic_group_step; destroy each member with ipic_destroy. */
+IPIC_API int  ipic_group_create(const ipic_props* props, const int* devices, int ndev, ipic_ctx** out_ctxs);
+IPIC_API int  ipic_group_step(ipic_ctx** ctxs, int n, uint64_t num_steps, uint32_t flags, double* t_first, double* t_rest);
 
 /* State transfer.  Replaces direct access to universe.cells / .field / .bcfield / .currentDensity
  * (universe.h:12-27).  `counts` has one entry per cell of the GLOBAL grid when the context is the
@@ -105,7 +122,7 @@ IPIC_API int  ipic_download_fields(ipic_ctx* ctx, double* field, double* bcfield
  * DurationMeasurement{firstStep, remainingSteps} (simulator.h:37-40). */
 IPIC_API int  ipic_step(ipic_ctx* ctx, uint64_t num_steps, uint32_t flags, double* t_first, double* t_rest);
 
-/* Same, but only enqueues the work on the context's stream(s); pair with ipic_sync. */
+/* Same, but only enqueues the work on the context's stream; pair with ipic_sync.  Single-GPU contexts only. */
 IPIC_API int  ipic_step_async(ipic_ctx* ctx, uint64_t num_steps, uint32_t flags);
 IPIC_API int  ipic_sync(ipic_ctx* ctx);
 

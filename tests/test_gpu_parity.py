@@ -285,3 +285,127 @@ def test_large_uniform_properties():
         assert c.count_misplaced() == 0
         c1, a1 = c.download_cells()
         assert int(c1.sum()) == len(aos)
+
+
+# ---- z-slab decomposition (in-process group: all slabs on this GPU, peer copies instead of NCCL) ---------
+
+def group_for(props, nslabs):
+    import allscale_ipic3d_b200 as ipic
+    return ipic.Group(props, [0] * nslabs)
+
+
+@pytest.mark.parametrize("nslabs", [2, 4])
+def test_slabs_small_dipole_match_single_context(golden_dir, nslabs):
+    """4^3 Earth dipole split into 2 (lz=2) and 4 (lz=1) z-slabs: every step bit-identical to the one-slab run,
+    incl. per-cell particle order (the face messages rebuild the neighbours' transfer buffers exactly)."""
+    g = np.load(os.path.join(golden_dir, "small_dipole.npz"))
+    props = load_props(g["props"])
+    with ctx_for(props) as one, group_for(props, nslabs) as grp:
+        one.upload_cells(g["counts0"], g["p0"])
+        grp.upload_cells(g["counts0"], g["p0"])
+        c0, a0 = grp.download_cells()
+        assert np.array_equal(c0, g["counts0"]) and bits_equal(a0, g["p0"])
+        for s in range(20):
+            one.step(1)
+            grp.step(1)
+            c1, a1 = one.download_cells()
+            c2, a2 = grp.download_cells()
+            assert np.array_equal(c1, c2), "step %d" % s
+            assert bits_equal(a1, a2), "step %d" % s
+        assert np.array_equal(c2, g["counts20"])
+        assert grp.count_misplaced() == one.count_misplaced()
+
+
+@pytest.mark.parametrize("n,nslabs,particles", [(6, 2, 40000), (6, 3, 40000), (6, 6, 20000), (2, 2, 3000), (8, 4, 60000)])
+def test_slabs_uniform_plasma_bit_exact(n, nslabs, particles):
+    """Uniform plasma with a big time step (heavy migration through every face, edge and corner, wall hits),
+    several steps per call (the exchange pipelines across steps): bit-exact vs the oracle."""
+    if not Ref.available():
+        pytest.skip("oracle/_ref not built")
+    props = Props.make(n, cellWidth=(10.0, 10.0, 10.0), dt=0.15 * 40)
+    r = Ref.uniform_grid(props, particles)
+    o = Oracle(props)
+    o.set_cells(r.counts(), r.particles())
+    with group_for(props, nslabs) as grp:
+        grp.upload_cells(r.counts(), r.particles())
+        for s in range(6):
+            grp.step(4)
+            o.step(4)
+            counts, aos = grp.download_cells()
+            assert np.array_equal(counts, o.counts()), "after %d steps" % (4 * (s + 1))
+            assert bits_equal(aos, o.particles()), "after %d steps" % (4 * (s + 1))
+
+
+@pytest.mark.parametrize("nslabs", [2, 8])
+def test_slabs_test_inp_counts(golden_dir, nslabs):
+    """inputs/test.inp over 2 and 8 slabs: per-cell counts bit-exact at every step vs the committed reference run."""
+    if not Ref.available():
+        pytest.skip("oracle/_ref not built")
+    g = np.load(os.path.join(golden_dir, "test_inp.npz"))
+    r = Ref.from_inp(os.path.join(golden_dir, "inputs", "test.inp"))
+    with group_for(r.props, nslabs) as grp:
+        grp.upload_cells(r.counts(), r.particles())
+        for s in range(1, 31):
+            grp.step(1)
+            assert np.array_equal(grp.cell_counts(), g["counts"][s]), "per-cell counts differ at step %d" % s
+
+
+@pytest.mark.parametrize("solver", ["forward", "leapfrog"])
+def test_slabs_full_pic_step_matches_single_context(golden_dir, solver):
+    """Interpolating mover + deposit + ghost update + solver on 2 slabs: J (all-gathered corner sums), fields and
+    particles bit-identical to the one-slab run; and the fused-deposit path of the analytic mover likewise."""
+    g = np.load(os.path.join(golden_dir, "small_fields.npz"))
+    props = load_props(g["props"])
+    nslabs = 2 if props.size[2] % 2 == 0 else int(props.size[2])
+    base = harness.PROJECT_CURRENT | harness.UPDATE_BOUNDARIES
+    base |= harness.SOLVER_FORWARD if solver == "forward" else harness.SOLVER_LEAPFROG
+    for flags in (base | harness.MOVER_INTERPOLATED, base):
+        with ctx_for(props) as one, group_for(props, nslabs) as grp:
+            for c in (one, grp):
+                c.upload_cells(g["counts0"], g["p0"])
+                c.upload_fields(g["field0"], g["bc0"], None)
+                c.step(3, flags)
+            c1, a1 = one.download_cells()
+            c2, a2 = grp.download_cells()
+            assert np.array_equal(c1, c2) and bits_equal(a1, a2)
+            for rank in range(nslabs):
+                for x, y in zip(one.download_fields(), grp.download_fields(rank)):
+                    assert bits_equal(x, y)
+
+
+def test_slabs_overflow_relayout():
+    """Slab contexts repair a cell-segment overflow on their own (re-layout + redo of that import) before anything
+    of the next step leaves the GPU: same convergence case as test_overflow_relayout, on 2 and 4 slabs."""
+    if not Ref.available():
+        pytest.skip("oracle/_ref not built")
+    props = Props.make(4, cellWidth=(10.0, 10.0, 10.0), dt=1.0)
+    r = Ref.uniform_grid(props, 64 * 700)
+    counts, aos = r.counts(), r.particles()
+    aos[:, 3:6] = 0.0
+    aos[:, 5] = np.where(aos[:, 2] < 20.0, 9.0, -9.0)     # everybody converges on the two middle z-planes: across slab faces
+    o = Oracle(props)
+    o.set_cells(counts, aos)
+    o.step(6)
+    for nslabs in (2, 4):
+        with group_for(props, nslabs) as grp:
+            grp.set_headroom(0.05, 32)
+            grp.upload_cells(counts, aos)
+            grp.step(6)
+            gc, ga = grp.download_cells()
+            assert grp.relayout_count() > 0
+        assert np.array_equal(gc, o.counts()) and bits_equal(ga, o.particles())
+
+
+def test_slabs_exchange_capacity_error():
+    """A face message that cannot hold the crossing particles fails loudly (no silent loss)."""
+    import allscale_ipic3d_b200 as ipic
+    if not Ref.available():
+        pytest.skip("oracle/_ref not built")
+    props = Props.make(4, cellWidth=(10.0, 10.0, 10.0), dt=0.15 * 40)
+    r = Ref.uniform_grid(props, 20000)
+    with group_for(props, 2) as grp:
+        grp.set_exchange_capacity(16)
+        grp.upload_cells(r.counts(), r.particles())
+        with pytest.raises(ipic.IpicError) as e:
+            grp.step(2)
+        assert e.value.code == -3 and "exchange" in str(e.value)
