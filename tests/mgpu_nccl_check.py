@@ -36,8 +36,6 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
-    uid = [ipic.Context.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
 
     def check(name, props, counts, aos, steps, batches, flags=0, fields=None):
         o = Oracle(props)
@@ -45,6 +43,8 @@ def main():
         if fields is not None:
             o.field(fields[0]); o.bcfield(fields[1])
         ctx = ipic.Context(props, device=local, rank=rank, nranks=world)
+        uid = [ipic.Context.comm_unique_id() if rank == 0 else None]      # an NCCL id serves one communicator
+        dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0])
         ctx.set_headroom(3.0, 256)
         idx, c0, a0 = slab_of(props, counts, aos, rank, world)
