@@ -600,14 +600,15 @@ int enqueueStepSingle(ipic_ctx* c, const StepFlags& f, int stepIndex) {
 //   BOUNDARY  mover on the two boundary planes, pack both faces                       [main stream]
 //   EXCHANGE  face messages to / from the z-neighbours (periodic)                     [comm stream]
 //   INTERIOR  mover on the interior planes -- overlaps the exchange                   [main stream]
-//   GATHER_J  all-gather of the slabs' per-cell corner sums, J on every rank, fields  [comm, main]
+//   GATHER_J  all-gather of the slabs' per-cell corner sums -- overlaps the imports     [comm stream]
 //   IMPORT    import interior planes; wait for the exchange; import the boundary planes,
 //             whose out-of-slab neighbours are columns of the received messages       [main stream]
+//   FIELDS    wait for the all-gather; J on every rank; ghost update + field solver   [main stream]
 //
 // (PRE_DEPOSIT / PRE_GATHER_J: the projection pass of the interpolating mode, which needs J and the
 // field update before the mover.)
 
-enum SlabPhase { PH_PRE_DEPOSIT, PH_PRE_GATHER_J, PH_BOUNDARY, PH_EXCHANGE, PH_INTERIOR, PH_GATHER_J, PH_IMPORT, PH_COUNT };
+enum SlabPhase { PH_PRE_DEPOSIT, PH_PRE_GATHER_J, PH_BOUNDARY, PH_EXCHANGE, PH_INTERIOR, PH_GATHER_J, PH_IMPORT, PH_FIELDS, PH_COUNT };
 
 size_t faceBytes(const ipic_ctx* c, int64_t cap) {
 	const int nxy = c->g.nx * c->g.ny;
@@ -682,6 +683,11 @@ int allGatherCellJ(ipic_ctx* c) {
 		}
 	}
 	CK(cudaEventRecord(c->evJ, c->commStream));
+	return IPIC_OK;
+}
+
+// main stream: wait for the all-gather, then the node-centric gather of J
+int finishCurrent(ipic_ctx* c) {
 	CK(cudaStreamWaitEvent(c->stream, c->evJ, 0));
 	launch_gather_current(c->g, c->dCellJ, c->dJ, c->dStop, c->stream);
 	c->launches++;
@@ -709,6 +715,7 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 	case PH_PRE_GATHER_J:
 		if (!(f.project && f.interp)) break;
 		{ int rc = allGatherCellJ(c); if (rc) return rc; }
+		{ int rc = finishCurrent(c); if (rc) return rc; }
 		break;
 	case PH_BOUNDARY: {
 		if (!f.fuseDeposit) fieldPhase(c, f);
@@ -758,7 +765,11 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 		break;
 	case PH_GATHER_J:
 		if (!f.fuseDeposit) break;
-		{ int rc = allGatherCellJ(c); if (rc) return rc; }
+		{ int rc = allGatherCellJ(c); if (rc) return rc; }      // on the comm stream, under the imports
+		break;
+	case PH_FIELDS:
+		if (!f.fuseDeposit) break;
+		{ int rc = finishCurrent(c); if (rc) return rc; }
 		fieldPhase(c, f);
 		break;
 	case PH_IMPORT:
