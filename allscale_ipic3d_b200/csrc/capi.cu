@@ -287,6 +287,17 @@ int ipic_device_count(int* count) {
 	return IPIC_OK;
 }
 
+int ipic_alloc_pinned(size_t bytes, void** out) {
+	if (!out) return fail(IPIC_ERR_ARG, "null argument");
+	CK(cudaMallocHost(out, bytes ? bytes : 1));
+	return IPIC_OK;
+}
+
+int ipic_free_pinned(void* p) {
+	if (p) CK(cudaFreeHost(p));
+	return IPIC_OK;
+}
+
 int ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, ipic_ctx** out) {
 	if (!props || !out) return fail(IPIC_ERR_ARG, "null argument");
 	if (nranks < 1 || rank < 0 || rank >= nranks) return fail(IPIC_ERR_ARG, "bad rank %d of %d", rank, nranks);

@@ -80,3 +80,139 @@ IPIC_API int ipic_host_uniform_particles(const ipic_props* p, uint64_t numPartic
 }
 
 }
+
+// ---- test hooks over the host C++ mirror (host/include/ipic3d/app) ----------------------------------------
+// Universes built by the mirror's own Parameters / initCells / initFields, exported in the C ABI's memory
+// formats so that tests/test_host_mirror.py can compare them bit for bit with the reference's.
+#include <cstring>
+#include <sstream>
+
+#include "ipic3d/app/benchmark.h"
+#include "ipic3d/app/universe.h"
+
+namespace {
+
+struct MirrorUniverse {
+	ipic3d::Universe universe;
+	std::uint64_t ncycles = 0, numParticles = 0;
+	explicit MirrorUniverse(ipic3d::Universe&& u) : universe(std::move(u)) {}
+};
+
+// main()'s set-up for "<file>.inp" (host/src/ipic3d.cc), without running anything
+MirrorUniverse* mirrorFromInp(const char* path) {
+	using namespace ipic3d;
+	const Parameters params{ std::string(path) };
+	const InitProperties initProperties(params);
+	UniverseProperties up(params);
+	up.dt = 0.01;
+	up.speedOfLight = 299792458;
+	up.planetRadius = 6378137;
+	up.cellWidth *= up.planetRadius;
+	const auto universeSize = elementwiseProduct(up.cellWidth, up.size);
+	up.objectCenter = { 0.0, 0.0, 0.0 };
+	up.origin = up.objectCenter - universeSize / 2.0;
+	up.externalMagneticField = { 0.0, 0.0, 3.07e-5 };
+	up.useCase = UseCase::Dipole;
+	int numParticles = (int)(up.size.x * up.size.y * up.size.z);
+	numParticles = numParticles * initProperties.particlesPerCell[0].x * initProperties.particlesPerCell[0].y * initProperties.particlesPerCell[0].z;
+	const double e = 1.602176565e-19, K = 1e7 * e, m = 1.672621777e-27;
+	const double v_mod = up.speedOfLight / std::sqrt(1.0 + (m * up.speedOfLight * up.speedOfLight) / K);
+	const auto low = up.origin + 0.125 * universeSize;
+	const auto hig = low + 0.75 * universeSize;
+	const auto dist = distribution::uniform_pos_normal_speed<>(low, hig, Vector3<double>{ 0, 0, 0 }, Vector3<double>{ v_mod, v_mod, v_mod });
+	auto* h = new MirrorUniverse(createUniverseFromDistribution(up, initProperties, numParticles, dist));
+	h->ncycles = params.ncycles;
+	h->numParticles = (std::uint64_t)numParticles;
+	return h;
+}
+
+} // namespace
+
+extern "C" {
+
+IPIC_API void* ipic_mirror_create_from_inp(const char* path, ipic_props* props, uint64_t* ncycles, uint64_t* numParticles) {
+	std::ostringstream quiet;
+	auto* old = std::cout.rdbuf(quiet.rdbuf());
+	MirrorUniverse* h = mirrorFromInp(path);
+	std::cout.rdbuf(old);
+	if (props) *props = h->universe.properties.toAbi();
+	if (ncycles) *ncycles = h->ncycles;
+	if (numParticles) *numParticles = h->numParticles;
+	return h;
+}
+
+// benchmark.h processDistribution's universe for `:U:N` (kind 'U'), `:C:N` ('C'), `:E:N` ('E'), `:B:N` ('B')
+IPIC_API void* ipic_mirror_create_benchmark(char kind, uint64_t numParticles, ipic_props* props) {
+	using namespace ipic3d;
+	std::ostringstream quiet;
+	auto* old = std::cout.rdbuf(quiet.rdbuf());
+	UniverseProperties up;
+	up.cellWidth = CELL_WIDTH; up.size = GRID_SIZE; up.dt = DELTA_T; up.FieldOutputCycle = 0;
+	InitProperties ip;
+	ip.driftVelocity.push_back(0);
+	MirrorUniverse* h = nullptr;
+	const Vector3<double> vlo{ -0.2, -0.2, -0.2 }, vhi{ +0.2, +0.2, +0.2 };
+	if (kind == 'U') h = new MirrorUniverse(createUniverseFromDistribution(up, ip, numParticles, distribution::uniform<>(Vector3<double>{ 0, 0, 0 }, UNIVERSE_SIZE, vlo, vhi)));
+	else if (kind == 'C') h = new MirrorUniverse(createUniverseFromDistribution(up, ip, numParticles, distribution::normal<>(UNIVERSE_SIZE / 2, UNIVERSE_SIZE / 5, vlo, vhi)));
+	else if (kind == 'B') h = new MirrorUniverse(createUniverseFromDistribution(up, ip, numParticles,
+		distribution::normal<>(UNIVERSE_SIZE / 100, UNIVERSE_SIZE / 500, UNIVERSE_SIZE / NUM_TIME_STEPS * 0.95 / DELTA_T, UNIVERSE_SIZE / NUM_TIME_STEPS * 0.95 / DELTA_T)));
+	else if (kind == 'E') {
+		using generator = distribution::generic_particle_generator<distribution::vector::uniform, distribution::vector::normal, distribution::species::electron>;
+		h = new MirrorUniverse(createUniverseFromDistribution(up, ip, numParticles,
+			distribution::make_spherical(generator({ UNIVERSE_SIZE * 0.4, UNIVERSE_SIZE * 0.6, 0 }, { Vector3<double>{ 0 }, Vector3<double>{ 1.5 }, 1 }, {}), UNIVERSE_SIZE / 2, UNIVERSE_SIZE.x / 10)));
+	}
+	std::cout.rdbuf(old);
+	if (h && props) *props = h->universe.properties.toAbi();
+	if (h) h->numParticles = numParticles;
+	return h;
+}
+
+IPIC_API void ipic_mirror_destroy(void* handle) { delete static_cast<MirrorUniverse*>(handle); }
+
+IPIC_API uint64_t ipic_mirror_total(void* handle) { return ipic3d::countParticlesInDomain(static_cast<MirrorUniverse*>(handle)->universe); }
+
+IPIC_API void ipic_mirror_get_counts(void* handle, uint64_t* counts) {
+	const auto& cells = static_cast<MirrorUniverse*>(handle)->universe.cells;
+	for (std::size_t i = 0; i < cells.count(); ++i) counts[i] = cells.data()[i].particles.size();
+}
+
+IPIC_API void ipic_mirror_get_particles(void* handle, double* aos) {
+	const auto& cells = static_cast<MirrorUniverse*>(handle)->universe.cells;
+	for (std::size_t i = 0; i < cells.count(); ++i) {
+		const auto& ps = cells.data()[i].particles;
+		if (!ps.empty()) std::memcpy(aos, ps.data(), ps.size() * sizeof(ipic3d::Particle));
+		aos += ps.size() * 8;
+	}
+}
+
+IPIC_API void ipic_mirror_get_fields(void* handle, double* field, double* bc, double* J) {
+	const auto& u = static_cast<MirrorUniverse*>(handle)->universe;
+	std::memcpy(field, u.field.data(), u.field.count() * sizeof(ipic3d::FieldNode));
+	std::memcpy(bc, u.bcfield.data(), u.bcfield.count() * sizeof(ipic3d::BcFieldCell));
+	std::memcpy(J, u.currentDensity.data(), u.currentDensity.count() * sizeof(ipic3d::DensityNode));
+}
+
+// the parser alone: values of every key the reference reads, as "name=value;" text (vectors comma separated)
+IPIC_API int ipic_mirror_parse(const char* path, char* out, int capacity) {
+	const ipic3d::Parameters p{ std::string(path) };
+	std::ostringstream s;
+	s.precision(17);
+	auto list = [&s](const char* name, const auto& v) { s << name << "="; for (std::size_t i = 0; i < v.size(); ++i) s << (i ? "," : "") << v[i]; s << ";"; };
+	s << "c=" << p.c << ";dt=" << p.dt << ";ncycles=" << p.ncycles << ";L=" << p.L.x << "," << p.L.y << "," << p.L.z
+	  << ";center=" << p.objectCenter.x << "," << p.objectCenter.y << "," << p.objectCenter.z << ";planetRadius=" << p.planetRadius
+	  << ";delta=" << p.delta << ";ncells=" << p.ncells.x << "," << p.ncells.y << "," << p.ncells.z
+	  << ";dspace=" << p.dspace.x << "," << p.dspace.y << "," << p.dspace.z << ";ns=" << p.ns
+	  << ";B0=" << p.B0.x << "," << p.B0.y << "," << p.B0.z << ";B1=" << p.B1.x << "," << p.B1.y << "," << p.B1.z
+	  << ";useCase=" << (p.useCase == ipic3d::UseCase::Dipole ? "Dipole" : "Test") << ";wmethod=" << p.wmethod << ";SimName=" << p.SimName
+	  << ";PoissonCorrection=" << p.PoissonCorrection << ";SaveDirName=" << p.SaveDirName << ";FieldOutputCycle=" << p.FieldOutputCycle
+	  << ";FieldOutputTag=" << p.FieldOutputTag << ";MomentsOutputTag=" << p.MomentsOutputTag << ";ParticlesOutputCycle=" << p.ParticlesOutputCycle
+	  << ";ParticlesOutputTag=" << p.ParticlesOutputTag << ";";
+	list("npcelx", p.npcelx); list("npcely", p.npcely); list("npcelz", p.npcelz); list("qom", p.qom); list("rhoInit", p.rhoInit);
+	list("uth", p.uth); list("vth", p.vth); list("wth", p.wth); list("u0", p.u0); list("v0", p.v0); list("w0", p.w0);
+	const std::string text = s.str();
+	if ((int)text.size() + 1 > capacity) return -1;
+	std::memcpy(out, text.c_str(), text.size() + 1);
+	return (int)text.size();
+}
+
+}

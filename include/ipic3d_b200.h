@@ -23,6 +23,7 @@
 #ifndef IPIC3D_B200_H
 #define IPIC3D_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__GNUC__)
@@ -73,6 +74,10 @@ typedef struct ipic_ctx ipic_ctx;
 IPIC_API const char* ipic_last_error(void);
 IPIC_API const char* ipic_version(void);
 IPIC_API int  ipic_device_count(int* count);
+
+/* Page-locked host memory for the AoS transfer buffers (so that uploads / downloads run at PCIe speed). */
+IPIC_API int  ipic_alloc_pinned(size_t bytes, void** out);
+IPIC_API int  ipic_free_pinned(void* p);
 
 /* Context: one z-slab of the universe on one GPU.  For a single GPU the slab is the whole
  * universe (rank 0 of 1).  Replaces the locals of simulateSteps (TransferBuffers, scratch;

@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <sstream>
 #include <string>
 
 #include "ipic3d/app/benchmark.h"
@@ -143,6 +144,52 @@ void* ref_create_uniform(uint64_t numParticles, ipic_props* outProps) {
 	auto universe = createUniverseFromDistribution(universeProperties, initProperties, numParticles, dist);
 	if (outProps) fromProps(universe.properties, outProps);
 	return new Handle(std::move(universe), initProperties);
+}
+
+// The other synthetic loads of processBenchmark (benchmark.h:94-138): 'C' cluster, 'E' explosion, 'B' beam, 'U' uniform.
+void* ref_create_benchmark(char kind, uint64_t numParticles, ipic_props* outProps) {
+	UniverseProperties universeProperties;
+	universeProperties.cellWidth = CELL_WIDTH;
+	universeProperties.size = GRID_SIZE;
+	universeProperties.dt = DELTA_T;
+	universeProperties.FieldOutputCycle = 0;
+	InitProperties initProperties;
+	initProperties.driftVelocity.push_back(0);
+	const uint64_t numTimeSteps = NUM_TIME_STEPS;
+	Handle* h = nullptr;
+	if (kind == 'U') return ref_create_uniform(numParticles, outProps);
+	if (kind == 'C') h = new Handle(createUniverseFromDistribution(universeProperties, initProperties, numParticles,
+		distribution::normal<>(UNIVERSE_SIZE / 2, UNIVERSE_SIZE / 5, Vector3<double>{ -0.2, -0.2, -0.2 }, Vector3<double>{ +0.2, +0.2, +0.2 })), initProperties);
+	if (kind == 'E') h = new Handle(createUniverseFromDistribution(universeProperties, initProperties, numParticles,
+		distribution::make_spherical(distribution::generic_particle_generator<distribution::vector::uniform, distribution::vector::normal, distribution::species::electron>(
+			{ UNIVERSE_SIZE * 0.4, UNIVERSE_SIZE * 0.6, 0 }, { Vector3<double>{ 0 }, Vector3<double>{ 1.5 }, 1 }, {}), UNIVERSE_SIZE / 2, UNIVERSE_SIZE.x / 10)), initProperties);
+	if (kind == 'B') h = new Handle(createUniverseFromDistribution(universeProperties, initProperties, numParticles,
+		distribution::normal<>(UNIVERSE_SIZE / 100, UNIVERSE_SIZE / 500, UNIVERSE_SIZE / numTimeSteps * 0.95 / DELTA_T, UNIVERSE_SIZE / numTimeSteps * 0.95 / DELTA_T)), initProperties);
+	if (h && outProps) fromProps(h->universe.properties, outProps);
+	return h;
+}
+
+// The reference's parser alone: every member it fills, as "name=value;" text (same format as the host mirror's hook).
+int ref_parse(const char* path, char* out, int capacity) {
+	const Parameters p{ std::string(path) };
+	std::ostringstream s;
+	s.precision(17);
+	auto list = [&s](const char* name, const auto& v) { s << name << "="; for (std::size_t i = 0; i < v.size(); ++i) s << (i ? "," : "") << v[i]; s << ";"; };
+	s << "c=" << p.c << ";dt=" << p.dt << ";ncycles=" << p.ncycles << ";L=" << p.L.x << "," << p.L.y << "," << p.L.z
+	  << ";center=" << p.objectCenter.x << "," << p.objectCenter.y << "," << p.objectCenter.z << ";planetRadius=" << p.planetRadius
+	  << ";delta=" << p.delta << ";ncells=" << p.ncells.x << "," << p.ncells.y << "," << p.ncells.z
+	  << ";dspace=" << p.dspace.x << "," << p.dspace.y << "," << p.dspace.z << ";ns=" << p.ns
+	  << ";B0=" << p.B0.x << "," << p.B0.y << "," << p.B0.z << ";B1=" << p.B1.x << "," << p.B1.y << "," << p.B1.z
+	  << ";useCase=" << (p.useCase == UseCase::Dipole ? "Dipole" : "Test") << ";wmethod=" << p.wmethod << ";SimName=" << p.SimName
+	  << ";PoissonCorrection=" << p.PoissonCorrection << ";SaveDirName=" << p.SaveDirName << ";FieldOutputCycle=" << p.FieldOutputCycle
+	  << ";FieldOutputTag=" << p.FieldOutputTag << ";MomentsOutputTag=" << p.MomentsOutputTag << ";ParticlesOutputCycle=" << p.ParticlesOutputCycle
+	  << ";ParticlesOutputTag=" << p.ParticlesOutputTag << ";";
+	list("npcelx", p.npcelx); list("npcely", p.npcely); list("npcelz", p.npcelz); list("qom", p.qom); list("rhoInit", p.rhoInit);
+	list("uth", p.uth); list("vth", p.vth); list("wth", p.wth); list("u0", p.u0); list("v0", p.v0); list("w0", p.w0);
+	const std::string text = s.str();
+	if ((int)text.size() + 1 > capacity) return -1;
+	std::memcpy(out, text.c_str(), text.size() + 1);
+	return (int)text.size();
 }
 
 // Same generator on an arbitrary cubic grid (for small-case parity tests).
