@@ -15,7 +15,8 @@
 //   Mover = interpolating_particle_mover       (extension) the commented corner-gather mover, cell.h:905-937
 //
 // The call uploads the universe, steps, and downloads it again, so callers may read and modify
-// `universe.cells[...]` / `universe.field[...]` between calls like the reference's tests do.
+// `universe.cells[...]` / `universe.field[...]` between calls like the reference's tests do.  GPU contexts
+// and the pinned staging buffer are kept between calls (releaseDevices() frees them).
 // GPUs: IPIC3D_GPUS=<n> (default 1) splits the universe into n z-slabs on devices 0..n-1 of this process;
 // IPIC3D_DEVICES=<ordinal,ordinal,...> names the slabs' devices explicitly.
 #pragma once
@@ -23,7 +24,9 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <iostream>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -58,6 +61,21 @@ namespace ipic3d {
 			std::exit(EXIT_FAILURE);
 		}
 
+		// host-side packing / unpacking of the per-cell vectors is plain memory traffic: spread it over the cores
+		template<typename Body>
+		void parallelFor(std::size_t tasks, const Body& body) {
+			unsigned workers = std::thread::hardware_concurrency();
+			if (const char* e = std::getenv("NUM_WORKERS")) workers = (unsigned)std::atoi(e);     // the reference's knob
+			workers = std::max(1u, std::min(workers, 64u));
+			if (tasks < 256 || workers == 1) { for (std::size_t t = 0; t < tasks; ++t) body(t); return; }
+			std::atomic<std::size_t> next(0);
+			auto work = [&]() { for (;;) { const std::size_t first = next.fetch_add(64); if (first >= tasks) return; for (std::size_t t = first; t < std::min(tasks, first + 64); ++t) body(t); } };
+			std::vector<std::thread> pool;
+			for (unsigned w = 1; w < workers; ++w) pool.emplace_back(work);
+			work();
+			for (auto& t : pool) t.join();
+		}
+
 		// CUDA ordinals of the slabs: IPIC3D_DEVICES="0,1,2,3" (ordinals may repeat: several slabs on one GPU),
 		// else the first IPIC3D_GPUS devices, else device 0.  Slabs hold whole z-planes.
 		inline std::vector<int> slabDevices(std::int64_t nz) {
@@ -83,15 +101,43 @@ namespace ipic3d {
 			return devices;
 		}
 
-		// pinned staging memory for the AoS transfers
-		struct PinnedBuffer {
-			void* p = nullptr; std::size_t bytes = 0;
-			explicit PinnedBuffer(std::size_t n) : bytes(n) { if (n) check(ipic_alloc_pinned(n, &p), "ipic_alloc_pinned"); }
-			~PinnedBuffer() { if (p) ipic_free_pinned(p); }
-			PinnedBuffer(const PinnedBuffer&) = delete;
-			PinnedBuffer& operator=(const PinnedBuffer&) = delete;
+		// Device contexts and the pinned staging buffer outlive a simulateSteps call: creating them costs far more
+		// than a time step, and drivers call simulateSteps repeatedly on the same universe (benchmark.h warm-up +
+		// timed run, the tests' simulateStep loops).  They are rebuilt when the universe's properties or the
+		// device list change, and released by releaseDevices() (or at process exit by the driver).
+		struct Session {
+			ipic_props abi{};
+			std::vector<int> devices;
+			std::vector<ipic_ctx*> ctx;
+			void* staging = nullptr;
+			std::uint64_t stagingParticles = 0;
+
+			void release() {
+				for (ipic_ctx* c : ctx) ipic_destroy(c);
+				ctx.clear();
+				if (staging) ipic_free_pinned(staging);
+				staging = nullptr; stagingParticles = 0;
+			}
+			void prepare(const ipic_props& props, const std::vector<int>& devs) {
+				if (!ctx.empty() && devs == devices && std::memcmp(&props, &abi, sizeof abi) == 0) return;
+				release();
+				abi = props; devices = devs;
+				ctx.assign(devs.size(), nullptr);
+				check(ipic_group_create(&abi, devices.data(), (int)devices.size(), ctx.data()), "ipic_group_create");
+			}
+			void reserveStaging(std::uint64_t particles) {
+				if (particles <= stagingParticles) return;
+				if (staging) ipic_free_pinned(staging);
+				staging = nullptr;
+				stagingParticles = particles + particles / 8;
+				check(ipic_alloc_pinned((std::size_t)stagingParticles * sizeof(Particle), &staging), "ipic_alloc_pinned");
+			}
+			static Session& instance() { static Session* s = new Session(); return *s; }   // never destroyed: CUDA may be gone at exit
 		};
 	}
+
+	// frees the GPU contexts and pinned memory kept between simulateSteps calls
+	inline void releaseDevices() { detail::Session::instance().release(); }
 
 	struct DurationMeasurement {
 		double firstStep;
@@ -118,8 +164,9 @@ namespace ipic3d {
 		const std::vector<int> devices = detail::slabDevices(nz);
 		const int gpus = (int)devices.size();
 		const std::int64_t lz = nz / gpus;
-		std::vector<ipic_ctx*> ctx((std::size_t)gpus, nullptr);
-		detail::check(ipic_group_create(&abi, devices.data(), gpus, ctx.data()), "ipic_group_create");
+		detail::Session& session = detail::Session::instance();
+		session.prepare(abi, devices);
+		std::vector<ipic_ctx*>& ctx = session.ctx;
 
 		// ---- upload: every slab's cells in slab order (x*ny + y)*lz + zl, particles cell-major as AoS records
 		std::vector<std::vector<std::uint64_t>> counts((std::size_t)gpus);
@@ -135,15 +182,22 @@ namespace ipic3d {
 			largestSlab = std::max(largestSlab, total);
 		}
 		// room for migration into a slab while it is on the device
-		const std::uint64_t stagingParticles = largestSlab + largestSlab / 4 + 65536;
-		detail::PinnedBuffer staging((std::size_t)stagingParticles * sizeof(Particle));
+		session.reserveStaging(largestSlab + largestSlab / 4 + 65536);
+		struct { void* p; } staging{ session.staging };
+		// slab cell c = (x*ny + y)*lz + zl  ->  the universe's cell
+		const auto cellOf = [&](int r, std::size_t c) -> Cell& {
+			const std::int64_t xy = (std::int64_t)c / lz, zl = (std::int64_t)c % lz;
+			return universe.cells[{ xy / ny, xy % ny, r * lz + zl }];
+		};
+		std::vector<std::uint64_t> offset;
 		for (int r = 0; r < gpus; ++r) {
-			char* out = static_cast<char*>(staging.p);
-			for (std::int64_t x = 0; x < nx; ++x) for (std::int64_t y = 0; y < ny; ++y) for (std::int64_t z = r * lz; z < (r + 1) * lz; ++z) {
-				const auto& ps = universe.cells[{ x, y, z }].particles;
-				if (!ps.empty()) std::memcpy(out, ps.data(), ps.size() * sizeof(Particle));
-				out += ps.size() * sizeof(Particle);
-			}
+			const auto& cnt = counts[(std::size_t)r];
+			offset.assign(cnt.size() + 1, 0);
+			for (std::size_t c = 0; c < cnt.size(); ++c) offset[c + 1] = offset[c] + cnt[c];
+			detail::parallelFor(cnt.size(), [&](std::size_t c) {
+				const auto& ps = cellOf(r, c).particles;
+				if (!ps.empty()) std::memcpy(static_cast<char*>(staging.p) + offset[c] * sizeof(Particle), ps.data(), ps.size() * sizeof(Particle));
+			});
 			detail::check(ipic_upload_cells(ctx[(std::size_t)r], counts[(std::size_t)r].data(), static_cast<const double*>(staging.p)), "ipic_upload_cells");
 			if (usesFields || writesCurrent)
 				detail::check(ipic_upload_fields(ctx[(std::size_t)r], reinterpret_cast<const double*>(universe.field.data()),
@@ -162,22 +216,21 @@ namespace ipic3d {
 			auto& cnt = counts[(std::size_t)r];
 			std::uint64_t total = 0;
 			detail::check(ipic_total_particles(ctx[(std::size_t)r], &total), "ipic_total_particles");
-			if (total > stagingParticles) { std::cerr << "ipic3d_b200: slab grew beyond the staging buffer" << std::endl; std::exit(EXIT_FAILURE); }
-			detail::check(ipic_download_cells(ctx[(std::size_t)r], cnt.data(), static_cast<double*>(staging.p), stagingParticles), "ipic_download_cells");
-			const char* in = static_cast<const char*>(staging.p);
-			std::size_t c = 0;
-			for (std::int64_t x = 0; x < nx; ++x) for (std::int64_t y = 0; y < ny; ++y) for (std::int64_t z = r * lz; z < (r + 1) * lz; ++z, ++c) {
-				auto& ps = universe.cells[{ x, y, z }].particles;
+			session.reserveStaging(total);
+			staging.p = session.staging;
+			detail::check(ipic_download_cells(ctx[(std::size_t)r], cnt.data(), static_cast<double*>(staging.p), session.stagingParticles), "ipic_download_cells");
+			offset.assign(cnt.size() + 1, 0);
+			for (std::size_t c = 0; c < cnt.size(); ++c) offset[c + 1] = offset[c] + cnt[c];
+			detail::parallelFor(cnt.size(), [&](std::size_t c) {
+				auto& ps = cellOf(r, c).particles;
 				ps.resize((std::size_t)cnt[c]);
-				if (cnt[c]) std::memcpy(ps.data(), in, (std::size_t)cnt[c] * sizeof(Particle));
-				in += cnt[c] * sizeof(Particle);
-			}
+				if (cnt[c]) std::memcpy(ps.data(), static_cast<const char*>(staging.p) + offset[c] * sizeof(Particle), (std::size_t)cnt[c] * sizeof(Particle));
+			});
 		}
 		if (writesFields || writesCurrent)     // the grids are replicated on every slab: rank 0 has them all
 			detail::check(ipic_download_fields(ctx[0], writesFields ? reinterpret_cast<double*>(universe.field.data()) : nullptr,
 			                                   writesFields ? reinterpret_cast<double*>(universe.bcfield.data()) : nullptr,
 			                                   writesCurrent ? reinterpret_cast<double*>(universe.currentDensity.data()) : nullptr), "ipic_download_fields");
-		for (ipic_ctx* c : ctx) ipic_destroy(c);
 		const auto endAll = clock::now();
 		return { seconds(endFirst - start), seconds(endAll - endFirst) };
 	}

@@ -22,7 +22,11 @@ int main(int argc, char** argv) {
 		return EXIT_FAILURE;
 	}
 	const std::string inputFilename = argv[1];
-	if (inputFilename[0] == ':') return processBenchmark(inputFilename);
+	if (inputFilename[0] == ':') {
+		const int rc = processBenchmark(inputFilename);
+		releaseDevices();
+		return rc;
+	}
 
 	std::cout << "Loading configuration file \"" << inputFilename << "\" ..." << std::endl;
 	const Parameters params(inputFilename);
@@ -68,5 +72,6 @@ int main(int argc, char** argv) {
 
 	std::cout << "Simulation finished successfully, producing output data..." << std::endl;
 	outputNumberOfParticlesPerCell(universe.cells, baseName + ".out");
+	releaseDevices();
 	return EXIT_SUCCESS;
 }
