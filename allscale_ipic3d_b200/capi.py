@@ -21,7 +21,7 @@ API_SYMBOLS = [
     "ipic_cell_counts", "ipic_total_particles", "ipic_upload_fields", "ipic_download_fields", "ipic_step",
     "ipic_step_async", "ipic_sync", "ipic_count_misplaced", "ipic_profile_reset", "ipic_profile_get", "ipic_selftest",
     "ipic_set_exchange_capacity", "ipic_group_create", "ipic_group_step", "ipic_relayout_count",
-    "ipic_alloc_pinned", "ipic_free_pinned",
+    "ipic_alloc_pinned", "ipic_free_pinned", "ipic_set_uniform_species", "ipic_particle_fields",
 ]
 
 
@@ -157,6 +157,14 @@ class Context:
     def relayout_count(self):
         t = C.c_uint64(0)
         self._ck(self.lib.ipic_relayout_count(self.h, C.byref(t)))
+        return int(t.value)
+
+    def set_uniform_species(self, enable):
+        self._ck(self.lib.ipic_set_uniform_species(self.h, C.c_int(1 if enable else 0)))
+
+    def particle_fields(self):
+        t = C.c_int(0)
+        self._ck(self.lib.ipic_particle_fields(self.h, C.byref(t)))
         return int(t.value)
 
     def upload_cells(self, counts, aos):
@@ -310,6 +318,13 @@ class Group:
     def set_exchange_capacity(self, particles):
         for m in self.members:
             m.set_exchange_capacity(particles)
+
+    def set_uniform_species(self, enable):
+        for m in self.members:
+            m.set_uniform_species(enable)
+
+    def particle_fields(self):
+        return [m.particle_fields() for m in self.members]
 
     def step(self, n=1, flags=0):
         a, b = C.c_double(0), C.c_double(0)

@@ -49,6 +49,8 @@ struct ipic_ctx {
 
 	// particle storage: two generations with a common layout
 	int64_t slots = 0;
+	int slotsNf = 0;                               // fields per particle the buffers were allocated for
+	bool allowUniformSpecies = true;               // ipic_set_uniform_species
 	ParticleArrays buf[2]{};
 	int cur = 0;                                   // generation holding the live particles
 	std::vector<int64_t> hCellStart;               // ncellsLocal + 1
@@ -97,7 +99,8 @@ struct ipic_ctx {
 	char* sendMsg[2] = { nullptr, nullptr };       // [0] face 0 -> slab below, [1] face 1 -> slab above
 	char* recvMsg[2] = { nullptr, nullptr };       // [0] from the slab below, [1] from the slab above
 	int* dFaceCnt = nullptr;
-	int64_t* dNegotiate = nullptr;                 // nranks x int64 scratch
+	int64_t* dNegotiate = nullptr;                 // nranks x SlabOffer scratch
+	bool emptyUpload = true;                       // the last upload held no particles
 	int* hStop = nullptr;                          // pinned mirror of dStop, refreshed after every slab step
 	cudaEvent_t evStepDone = nullptr;
 };
@@ -114,11 +117,12 @@ void freeParticleBuffers(ipic_ctx* c) {
 	if (c->dTag) cudaFree(c->dTag);
 	c->dTag = nullptr;
 	c->slots = 0;
+	c->slotsNf = 0;
 }
 
-int allocParticleBuffers(ParticleArrays out[2], unsigned char** tag, int64_t slots) {
-	// slots is a multiple of 32: whole AoSoA-32 blocks of 2 KiB
-	for (int b = 0; b < 2; b++) CK(cudaMalloc(&out[b].d, (size_t)std::max<int64_t>(slots, 32) * kFields * sizeof(double)));
+int allocParticleBuffers(ParticleArrays out[2], unsigned char** tag, int64_t slots, int nf) {
+	// slots is a multiple of 32: whole AoSoA-32 blocks of 32*nf doubles
+	for (int b = 0; b < 2; b++) CK(cudaMalloc(&out[b].d, (size_t)std::max<int64_t>(slots, 32) * nf * sizeof(double)));
 	CK(cudaMalloc(tag, (size_t)std::max<int64_t>(slots, 1)));
 	return IPIC_OK;
 }
@@ -174,17 +178,16 @@ void fillGeometry(ipic_ctx* c) {
 	g.magTemp = -p.externalMagneticField[2] * std::pow(p.planetRadius, 3);   // host libm, as the reference (cell.h:919)
 	g.pic = M_PI * p.speedOfLight;                                           // cell.h:949
 	g.vol = p.cellWidth[0] * p.cellWidth[1] * p.cellWidth[2];
+	g.nf = kFields; g.uq = 0.0; g.uqom = 0.0;
 }
 
 // Tile shape of the mover (measured on B200, profiles/README.md): the kernel is bound by how many warps
 // are resident, so one particle per thread (72 / 96 registers, 7 / 5 CTAs per SM) wins over two, and few
 // stages win over many (shared memory caps the CTAs per SM): 2 stages = 16 KiB for the plain mover; with
 // the fused deposit a batch of 4 stages amortises the per-batch block reduction of the 24 corner sums.
-void pickTileShape(const ipic_ctx* c, bool deposit, int& items, int& stages) {
+void pickTileShape(const ipic_ctx* c, bool deposit, int& stages) {
 	const int64_t avg = c->meanPopulation;
-	items = 1;
-	if (const char* e = std::getenv("IPIC_ITEMS")) { const int v = std::atoi(e); if (v == 1 || v == 2) items = v; }     // tuning knob
-	const int64_t tile = (int64_t)items * 128;
+	const int64_t tile = 128;
 	stages = (int)std::max<int64_t>(1, std::min<int64_t>((avg + avg / 8 + tile - 1) / tile, deposit ? 4 : 2));
 	if (const char* e = std::getenv("IPIC_STAGES")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) stages = v; }   // tuning knob
 }
@@ -247,7 +250,7 @@ int relayoutAfterOverflow(ipic_ctx* c, int outGen, int failedStep) {
 	buildLayout(c, need64, newStart);
 	ParticleArrays nb[2]{}; unsigned char* ntag = nullptr;
 	const int64_t nslots = newStart.back();
-	rc = allocParticleBuffers(nb, &ntag, nslots);
+	rc = allocParticleBuffers(nb, &ntag, nslots, c->g.nf);
 	if (rc) return rc;
 	int64_t* dNewStart = nullptr;
 	CK(cudaMalloc(&dNewStart, newStart.size() * sizeof(int64_t)));
@@ -255,7 +258,7 @@ int relayoutAfterOverflow(ipic_ctx* c, int outGen, int failedStep) {
 	CK(cudaMemsetAsync(c->dStop, 0, 4 * sizeof(int), c->stream));
 	int big = 0x7fffffff;
 	CK(cudaMemcpyAsync(c->dStop + 1, &big, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-	launch_copy_heads(c->g, c->buf[outGen], c->dCellStart, nb[outGen], dNewStart, c->dStay, c->stream);
+	launch_copy_heads(c->g, c->buf[outGen], c->dCellStart, nb[outGen], dNewStart, c->dStay, c->g.nf, c->g.uq, c->g.uqom, c->stream);
 	ImportArgs ia{};
 	ia.g = c->g; ia.src = c->buf[outGen]; ia.srcStart = c->dCellStart; ia.srcLeave = c->dLeave; ia.tag = c->dTag;
 	ia.dst = nb[outGen]; ia.dstStart = dNewStart; ia.stay = c->dStay; ia.dstCount = c->dCount;
@@ -269,8 +272,28 @@ int relayoutAfterOverflow(ipic_ctx* c, int outGen, int failedStep) {
 	// swap in the new storage
 	freeParticleBuffers(c);
 	cudaFree(c->dCellStart);
-	c->buf[0] = nb[0]; c->buf[1] = nb[1]; c->dTag = ntag; c->dCellStart = dNewStart; c->slots = nslots; c->hCellStart = newStart;
+	c->buf[0] = nb[0]; c->buf[1] = nb[1]; c->dTag = ntag; c->dCellStart = dNewStart; c->slots = nslots; c->slotsNf = c->g.nf; c->hCellStart = newStart;
 	if (stop[0]) return fail(IPIC_ERR_INTERNAL, "relayout did not resolve the overflow of step %d", failedStep);
+	return IPIC_OK;
+}
+
+// Leave the uniform-species layout: same segments, 8 fields per particle, q and qom materialised.  Needed when
+// slabs turn out to carry different species (the live generation is converted; the other one is scratch).
+int convertToFullLayout(ipic_ctx* c) {
+	if (c->g.nf == kFields) return IPIC_OK;
+	CK(cudaSetDevice(c->device));
+	ParticleArrays nb[2]{}; unsigned char* ntag = nullptr;
+	int rc = allocParticleBuffers(nb, &ntag, c->slots, kFields);
+	if (rc) return rc;
+	Geometry wide = c->g;
+	wide.nf = kFields;
+	launch_copy_heads(wide, c->buf[c->cur], c->dCellStart, nb[c->cur], c->dCellStart, c->dCount, c->g.nf, c->g.uq, c->g.uqom, c->stream);
+	c->launches++;
+	CK(cudaStreamSynchronize(c->stream));
+	const int64_t slots = c->slots;
+	freeParticleBuffers(c);
+	c->buf[0] = nb[0]; c->buf[1] = nb[1]; c->dTag = ntag; c->slots = slots; c->slotsNf = kFields;
+	c->g = wide;
 	return IPIC_OK;
 }
 
@@ -344,7 +367,7 @@ int ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, 
 		CK(cudaStreamCreateWithFlags(&c->commStream, cudaStreamNonBlocking));
 		for (cudaEvent_t* e : { &c->evPacked, &c->evRecv, &c->evMoved, &c->evJ }) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 		CK(cudaMalloc(&c->dFaceCnt, (size_t)2 * g.nx * g.ny * sizeof(int)));
-		CK(cudaMalloc(&c->dNegotiate, (size_t)nranks * sizeof(int64_t)));
+		CK(cudaMalloc(&c->dNegotiate, (size_t)nranks * 4 * sizeof(int64_t)));
 		CK(cudaMallocHost(&c->hStop, 4 * sizeof(int)));
 		CK(cudaEventCreateWithFlags(&c->evStepDone, cudaEventDisableTiming));
 	}
@@ -394,6 +417,18 @@ int ipic_set_exchange_capacity(ipic_ctx* c, int64_t particles) {
 	return IPIC_OK;
 }
 
+int ipic_set_uniform_species(ipic_ctx* c, int enable) {
+	if (!c) return fail(IPIC_ERR_ARG, "null context");
+	c->allowUniformSpecies = enable != 0;
+	return IPIC_OK;
+}
+
+int ipic_particle_fields(ipic_ctx* c, int* fields) {
+	if (!c || !fields) return fail(IPIC_ERR_ARG, "null argument");
+	*fields = c->g.nf;
+	return IPIC_OK;
+}
+
 int ipic_upload_cells(ipic_ctx* c, const uint64_t* counts, const double* aos) {
 	if (!c || !counts) return fail(IPIC_ERR_ARG, "null argument");
 	CK(cudaSetDevice(c->device));
@@ -408,28 +443,46 @@ int ipic_upload_cells(ipic_ctx* c, const uint64_t* counts, const double* aos) {
 	}
 	const int64_t total = aosStart[nOwned];
 	if (total > 0 && !aos) return fail(IPIC_ERR_ARG, "particles_aos is null");
+	// stage the AoS records on the device and look at the species: one (q, qom) for all particles -> 6-field layout
+	int rc = ensureStage(c, total * 8 + 8);
+	if (rc) return rc;
+	int nf = kFields;
+	double uq = 0.0, uqom = 0.0;
+	if (total) {
+		CK(cudaMemcpyAsync(c->dStage, aos, (size_t)total * 64, cudaMemcpyHostToDevice, c->stream));
+		if (c->allowUniformSpecies) {
+			int* dFlag = reinterpret_cast<int*>(c->dStage + total * 8);
+			CK(cudaMemsetAsync(dFlag, 0, sizeof(int), c->stream));
+			launch_check_species(c->dStage, total, dFlag, c->stream);
+			c->launches++;
+			int mixed = 1;
+			CK(cudaMemcpyAsync(&mixed, dFlag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+			CK(cudaStreamSynchronize(c->stream));
+			if (!mixed) { nf = 6; uq = aos[6]; uqom = aos[7]; }
+		}
+	}
+	c->g.nf = nf; c->g.uq = uq; c->g.uqom = uqom;
 	std::vector<int64_t> start;
 	buildLayout(c, need, start);
-	if (start.back() > c->slots || start.back() < c->slots / 2) {
+	if (start.back() > c->slots || start.back() < c->slots / 2 || c->slotsNf != nf) {
 		freeParticleBuffers(c);
-		int rc = allocParticleBuffers(c->buf, &c->dTag, start.back());
+		rc = allocParticleBuffers(c->buf, &c->dTag, start.back(), nf);
 		if (rc) return rc;
 		c->slots = start.back();
+		c->slotsNf = nf;
 	}
 	c->hCellStart = start;
 	CK(cudaMemcpyAsync(c->dCellStart, start.data(), start.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
 	CK(cudaMemcpyAsync(c->dAosStart, aosStart.data(), aosStart.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
 	CK(cudaMemcpyAsync(c->dCount, localCount.data(), localCount.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
 	CK(cudaMemsetAsync(c->dLeave, 0, (size_t)c->g.ncellsLocal * sizeof(int), c->stream));
-	int rc = ensureStage(c, total * 8);
-	if (rc) return rc;
 	if (total) {
-		CK(cudaMemcpyAsync(c->dStage, aos, (size_t)total * 64, cudaMemcpyHostToDevice, c->stream));
 		launch_scatter_aos(c->g, c->dStage, c->dAosStart, c->buf[c->cur], c->dCellStart, c->stream);
 		c->launches++;
 	}
 	CK(cudaStreamSynchronize(c->stream));     // host vectors above go out of scope
 	c->haveCells = true;
+	c->emptyUpload = total == 0;
 	c->meanPopulation = total / std::max(1, nOwned);
 	if (c->nranks > 1) {
 		int64_t lo = 0, hi = 0;
@@ -543,7 +596,7 @@ MoveArgs moveArgs(ipic_ctx* c, const StepFlags& f, int zBegin, int zCount) {
 	ma.fieldEB = c->dEB; ma.cellJ = c->dCellJ; ma.stopFlag = c->dStop;
 	ma.zBegin = zBegin; ma.zCount = zCount;
 	ma.interpolate = f.interp; ma.migrate = f.migrate; ma.push = true; ma.deposit = f.fuseDeposit;
-	pickTileShape(c, ma.deposit, ma.itemsPerThread, ma.stages);
+	pickTileShape(c, ma.deposit, ma.stages);
 	return ma;
 }
 
@@ -556,7 +609,7 @@ void fieldPhase(ipic_ctx* c, const StepFlags& f) {
 void depositPass(ipic_ctx* c, const StepFlags& f, int zBegin, int zCount) {
 	MoveArgs da = moveArgs(c, f, zBegin, zCount);
 	da.push = false; da.deposit = true; da.interpolate = false;
-	pickTileShape(c, true, da.itemsPerThread, da.stages);
+	pickTileShape(c, true, da.stages);
 	launch_move(da, c->stream);
 	c->launches++;
 }
@@ -648,28 +701,70 @@ int allocExchange(ipic_ctx* c, int64_t cap) {
 	return IPIC_OK;
 }
 
-// all ranks agree on max(wanted capacity); NCCL contexts must all enter this in the same ipic_step call
+// What a slab contributes to the negotiation before the first step after an upload: the face-message capacity
+// it wants, and its species state (0 = no particles, 6 = one species with the (q, qom) bits that follow, 8 = mixed).
+struct SlabOffer { int64_t cap, species, qBits, qomBits; };
+
+SlabOffer offerOf(const ipic_ctx* c) {
+	SlabOffer o;
+	o.cap = wantedMsgCap(c);
+	o.species = c->emptyUpload ? 0 : c->g.nf;
+	std::memcpy(&o.qBits, &c->g.uq, 8);
+	std::memcpy(&o.qomBits, &c->g.uqom, 8);
+	return o;
+}
+
+// All slabs use the same particle layout: 6 fields only if every slab that holds particles holds the same single
+// species (arrivals from a neighbour must fit the layout); empty slabs adopt it; otherwise everybody widens to 8.
+int agreeOnLayout(ipic_ctx* c, const std::vector<SlabOffer>& all) {
+	bool uniform = true, any = false;
+	int64_t q = 0, m = 0;
+	for (const SlabOffer& o : all) {
+		if (o.species == 0) continue;
+		if (o.species != 6) { uniform = false; break; }
+		if (!any) { q = o.qBits; m = o.qomBits; any = true; }
+		else if (o.qBits != q || o.qomBits != m) { uniform = false; break; }
+	}
+	if (!uniform || !any) return convertToFullLayout(c);
+	if (c->g.nf == kFields) {          // an empty slab: its (8-field sized) buffers are roomy enough for the 6-field layout
+		c->g.nf = 6;
+		std::memcpy(&c->g.uq, &q, 8);
+		std::memcpy(&c->g.uqom, &m, 8);
+	}
+	return IPIC_OK;
+}
+
+// all ranks agree on max(wanted capacity) and on the layout; NCCL contexts must all enter this in the same ipic_step call
 int negotiateExchangeNccl(ipic_ctx* c) {
 	if (!c->exchangeDirty) return IPIC_OK;
 	CK(cudaSetDevice(c->device));
-	std::vector<int64_t> all((size_t)c->nranks, 0);
-	const int64_t mine = wantedMsgCap(c);
-	CK(cudaMemcpyAsync(c->dNegotiate + c->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, c->commStream));
-	int rc = comm_allgather(c->comm, c->dNegotiate + c->rank, c->dNegotiate, sizeof(int64_t), c->commStream, g_lastError);
+	std::vector<SlabOffer> all((size_t)c->nranks);
+	const SlabOffer mine = offerOf(c);
+	SlabOffer* d = reinterpret_cast<SlabOffer*>(c->dNegotiate);
+	CK(cudaMemcpyAsync(d + c->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, c->commStream));
+	int rc = comm_allgather(c->comm, d + c->rank, d, sizeof(SlabOffer), c->commStream, g_lastError);
 	if (rc) return rc;
-	CK(cudaMemcpyAsync(all.data(), c->dNegotiate, all.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, c->commStream));
+	CK(cudaMemcpyAsync(all.data(), d, all.size() * sizeof(SlabOffer), cudaMemcpyDeviceToHost, c->commStream));
 	CK(cudaStreamSynchronize(c->commStream));
 	int64_t cap = 0;
-	for (int64_t v : all) cap = std::max(cap, v);
+	for (const SlabOffer& o : all) cap = std::max(cap, o.cap);
+	rc = agreeOnLayout(c, all);
+	if (rc) return rc;
 	return allocExchange(c, cap);
 }
 
 int negotiateExchangeGroup(ipic_group* grp) {
 	bool dirty = false;
+	std::vector<SlabOffer> all;
 	int64_t cap = 0;
-	for (ipic_ctx* m : grp->members) { dirty = dirty || m->exchangeDirty; cap = std::max(cap, wantedMsgCap(m)); }
+	for (ipic_ctx* m : grp->members) { dirty = dirty || m->exchangeDirty; all.push_back(offerOf(m)); cap = std::max(cap, all.back().cap); }
 	if (!dirty) return IPIC_OK;
-	for (ipic_ctx* m : grp->members) { int rc = allocExchange(m, cap); if (rc) return rc; }
+	for (ipic_ctx* m : grp->members) {
+		int rc = agreeOnLayout(m, all);
+		if (rc) return rc;
+		rc = allocExchange(m, cap);
+		if (rc) return rc;
+	}
 	return IPIC_OK;
 }
 

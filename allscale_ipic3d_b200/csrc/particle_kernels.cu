@@ -75,15 +75,17 @@ constexpr int kMaxStages = 8;
 #define IPIC_MINB_NODEP 7
 #endif
 
-template<int ITEMS, bool INTERP, bool DEPOSIT, bool MIGRATE, bool PUSH>
+template<int NF, bool INTERP, bool DEPOSIT, bool MIGRATE, bool PUSH>
 __global__ void __launch_bounds__(kBlock, DEPOSIT ? IPIC_MINB_DEP : IPIC_MINB_NODEP)
 k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, const int64_t* __restrict__ cellStart,
        const int* __restrict__ countIn, int* __restrict__ countOut, int* __restrict__ nLeave,
        unsigned char* __restrict__ tag, const double* __restrict__ fieldEB, double* __restrict__ cellJ,
        const int* __restrict__ stopFlag, int zBegin, int zCount, int stages) {
 
+	constexpr int ITEMS = 1;                                     // particles per thread per tile (one wins: more resident warps)
 	constexpr int TILE = ITEMS * kBlock;
-	constexpr int TILE_DOUBLES = TILE * kFields;
+	constexpr int TILE_DOUBLES = TILE * NF;
+	constexpr int BLOCK_DOUBLES = 32 * NF;                       // one AoSoA block
 
 	if (*stopFlag) return;
 
@@ -104,8 +106,8 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	const int n = countIn[cell];
 	const int64_t base = cellStart[cell];
 	const int cap = (int)(cellStart[cell + 1] - base);
-	const double* __restrict__ src = in.d + (base << 3);         // base is a multiple of 32 slots
-	double* __restrict__ dst = out.d + (base << 3);
+	const double* __restrict__ src = in.d + base * NF;           // base is a multiple of 32 slots
+	double* __restrict__ dst = out.d + base * NF;
 	const int nTiles = (n + TILE - 1) / TILE;
 
 	if (DEPOSIT && tid < 24) sJ[tid] = 0.0;
@@ -119,9 +121,9 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	auto issue = [&](int t, int s) {
 		const int first = t * TILE;
 		const int cnt = min(TILE, n - first);
-		const uint32_t bytes = (uint32_t)((cnt + 31) >> 5) * (32 * kFields * 8);
+		const uint32_t bytes = (uint32_t)((cnt + 31) >> 5) * (BLOCK_DOUBLES * 8);
 		mbar_expect_tx(&sFull[s], bytes);
-		tma_bulk_g2s(sTile + s * TILE_DOUBLES, src + (int64_t)first * kFields, bytes, &sFull[s]);
+		tma_bulk_g2s(sTile + s * TILE_DOUBLES, src + (int64_t)first * NF, bytes, &sFull[s]);
 	};
 	if (tid == 0) {
 		const int pre = min(stages, nTiles);
@@ -175,14 +177,14 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 				#pragma unroll
 				for (int k = 0; k < ITEMS; k++) {
 					if ((tb + b) * TILE + k * kBlock + tid < n) {
-						const double* p = tile + ((k * kWarps + warp) << 8) + lane;
+						const double* p = tile + (k * kWarps + warp) * BLOCK_DOUBLES + lane;
 						// projectToDensityField weights (reference cell.h:810-816); corner (a,b,c) of this cell is the
 						// node the reference reaches with (i,j,k) = (-a,-b,-c).  The per-cell sums are accumulated in
 						// a different order than the reference's sequential loop anyway, so this part uses a
 						// reciprocal multiply and FMAs (J is compared at 1e-12, not bit for bit).
 						const double rx = (p[0] - org[0]) * g.iw[0], ry = (p[32] - org[1]) * g.iw[1], rz = (p[64] - org[2]) * g.iw[2];
 						const double ox = 1.0 - rx, oy = 1.0 - ry, oz = 1.0 - rz;
-						const double q = p[192];
+						const double q = NF == 8 ? p[192] : g.uq;
 						const double jx = q * p[96], jy = q * p[128], jz = q * p[160];
 						const double wxy[4] = { ox * oy, ox * ry, rx * oy, rx * ry };
 						#pragma unroll
@@ -235,10 +237,10 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 			#pragma unroll
 			for (int k = 0; k < ITEMS; k++) {
 				if (c0 + k * kBlock + tid < n) {
-					const double* p = tile + ((k * kWarps + warp) << 8) + lane;
+					const double* p = tile + (k * kWarps + warp) * BLOCK_DOUBLES + lane;
 					px[k] = p[0]; py[k] = p[32]; pz[k] = p[64];
 					vx[k] = p[96]; vy[k] = p[128]; vz[k] = p[160];
-					pq[k] = p[192]; pm[k] = p[224];
+					if (NF == 8) { pq[k] = p[192]; pm[k] = p[224]; } else { pq[k] = g.uq; pm[k] = g.uqom; }
 				}
 			}
 			#pragma unroll
@@ -290,10 +292,10 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 						d = cap - 1 - (left + (mine[k] >> 16) + __popc(bl[k] & lt));
 						tag[base + d] = (unsigned char)code[k];
 					}
-					double* q = dst + ((int64_t)(d >> 5) << 8) + (d & 31);
+					double* q = dst + (int64_t)(d >> 5) * BLOCK_DOUBLES + (d & 31);
 					st_stream(q, px[k]); st_stream(q + 32, py[k]); st_stream(q + 64, pz[k]);
 					st_stream(q + 96, vx[k]); st_stream(q + 128, vy[k]); st_stream(q + 160, vz[k]);
-					st_stream(q + 192, pq[k]); st_stream(q + 224, pm[k]);
+					if (NF == 8) { st_stream(q + 192, pq[k]); st_stream(q + 224, pm[k]); }
 				}
 			}
 			kept += run & 0xffff; left += run >> 16;
@@ -327,20 +329,21 @@ struct ImportSource {
 	const unsigned char* tags;
 	const double* data;
 	bool remote;
+	int nf;
 	__device__ __forceinline__ unsigned char tagOf(int64_t base, int j) const { return remote ? tags[base + j] : tags[base - j]; }
 	__device__ __forceinline__ void copyTo(int64_t base, int j, double* __restrict__ t) const {
 		double v[kFields];
-		if (remote) {
+		if (remote) {                                    // message records always carry all 8 fields
 			const double2* s = reinterpret_cast<const double2*>(data + (base + j) * kFields);
 			#pragma unroll
 			for (int f = 0; f < kFields; f += 2) { const double2 x = s[f >> 1]; v[f] = x.x; v[f + 1] = x.y; }
 		} else {
-			const double* s = data + slot_index(base - j);
+			const double* s = data + slot_index(base - j, nf);
 			#pragma unroll
-			for (int f = 0; f < kFields; f++) v[f] = s[f * kFieldStride];
+			for (int f = 0; f < kFields; f++) if (f < nf) v[f] = s[f * kFieldStride];
 		}
 		#pragma unroll
-		for (int f = 0; f < kFields; f++) t[f * kFieldStride] = v[f];
+		for (int f = 0; f < kFields; f++) if (f < nf) t[f * kFieldStride] = v[f];
 	}
 };
 
@@ -368,6 +371,7 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 	// source of direction d (uniform over the warp): the local outbox, or a column of a face message
 	auto sourceOf = [&](int d) {
 		ImportSource s;
+		s.nf = g.nf;
 		const int c = d % 3;
 		s.remote = SLAB && ((c == 0 && zl == 0) || (c == 2 && zl == g.lz - 1));
 		if (s.remote) { const FaceMsg& m = c == 0 ? fromDown : fromUp; s.tags = m.tags; s.data = m.particles; }
@@ -437,7 +441,7 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 				pre += cnt;
 			}
 			const int64_t base = __shfl_sync(0xffffffffu, myBase, dsel);
-			if (i < total && w + i < room) sourceOf(dsel).copyTo(base, jsel, dst.d + slot_index(dbase + w + i));
+			if (i < total && w + i < room) sourceOf(dsel).copyTo(base, jsel, dst.d + slot_index(dbase + w + i, g.nf));
 		}
 		w += total;
 	} else {
@@ -455,7 +459,7 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 				const unsigned m = __ballot_sync(0xffffffffu, hit);
 				if (hit) {
 					const int o = w + __popc(m & ((1u << lane) - 1u));
-					if (o < room) s.copyTo(base, j, dst.d + slot_index(dbase + o));
+					if (o < room) s.copyTo(base, j, dst.d + slot_index(dbase + o, g.nf));
 				}
 				w += __popc(m);
 			}
@@ -570,10 +574,11 @@ k_face_copy(const Geometry g, const ParticleArrays src, const int64_t* __restric
 		if (hit) {
 			const int o = first + w + __popc(mask & ((1u << lane) - 1u));
 			if (o < m.cap) {
-				const double* s = src.d + slot_index(send - j);
+				const double* s = src.d + slot_index(send - j, g.nf);
 				double v[kFields];
+				v[6] = g.uq; v[7] = g.uqom;
 				#pragma unroll
-				for (int k = 0; k < kFields; k++) v[k] = s[k * kFieldStride];
+				for (int k = 0; k < kFields; k++) if (k < g.nf) v[k] = s[k * kFieldStride];
 				double2* d = reinterpret_cast<double2*>(m.particles + (int64_t)o * kFields);
 				#pragma unroll
 				for (int k = 0; k < kFields; k += 2) d[k >> 1] = make_double2(v[k], v[k + 1]);
@@ -619,7 +624,7 @@ __global__ void k_count_misplaced(const Geometry g, const ParticleArrays p, cons
 	const int64_t base = cellStart[cell];
 	unsigned long long local = 0;
 	for (int i = threadIdx.x; i < count[cell]; i += blockDim.x) {
-		const double* q = p.d + slot_index(base + i);
+		const double* q = p.d + slot_index(base + i, g.nf);
 		const bool ok = fabs(q[0] - c0) <= g.hw[0] && fabs(q[kFieldStride] - c1) <= g.hw[1] && fabs(q[2 * kFieldStride] - c2) <= g.hw[2];
 		if (!ok) local++;
 	}
@@ -636,7 +641,8 @@ __global__ void k_scatter_aos(const Geometry g, const double* __restrict__ aos, 
 	const int zl = oc % g.lz, xy = oc / g.lz;
 	const int cell = xy * g.lz + zl;
 	const int64_t a0 = aosStart[oc], n = aosStart[oc + 1] - a0, base = cellStart[cell];
-	for (int64_t e = threadIdx.x; e < n * 8; e += blockDim.x) p.d[slot_index(base + (e >> 3)) + (e & 7) * kFieldStride] = aos[a0 * 8 + e];
+	for (int64_t e = threadIdx.x; e < n * 8; e += blockDim.x)
+		if ((int)(e & 7) < g.nf) p.d[slot_index(base + (e >> 3), g.nf) + (e & 7) * kFieldStride] = aos[a0 * 8 + e];
 }
 
 __global__ void k_gather_aos(const Geometry g, double* __restrict__ aos, const int64_t* __restrict__ aosStart,
@@ -645,22 +651,35 @@ __global__ void k_gather_aos(const Geometry g, double* __restrict__ aos, const i
 	const int zl = oc % g.lz, xy = oc / g.lz;
 	const int cell = xy * g.lz + zl;
 	const int64_t a0 = aosStart[oc], n = aosStart[oc + 1] - a0, base = cellStart[cell];
-	for (int64_t e = threadIdx.x; e < n * 8; e += blockDim.x) aos[a0 * 8 + e] = p.d[slot_index(base + (e >> 3)) + (e & 7) * kFieldStride];
+	for (int64_t e = threadIdx.x; e < n * 8; e += blockDim.x) {
+		const int f = (int)(e & 7);
+		aos[a0 * 8 + e] = f < g.nf ? p.d[slot_index(base + (e >> 3), g.nf) + f * kFieldStride] : (f == 6 ? g.uq : g.uqom);
+	}
 }
 
 // copy the live head of every owned cell from one layout to another (relayout)
 __global__ void k_copy_heads(const Geometry g, const ParticleArrays src, const int64_t* __restrict__ srcStart,
-                             const ParticleArrays dst, const int64_t* __restrict__ dstStart, const int* __restrict__ count) {
+                             const ParticleArrays dst, const int64_t* __restrict__ dstStart, const int* __restrict__ count,
+                             int srcNf, double srcQ, double srcQom) {
 	const int oc = blockIdx.x;
 	const int zl = oc % g.lz, xy = oc / g.lz;
 	const int cell = xy * g.lz + zl;
 	const int64_t s0 = srcStart[cell], d0 = dstStart[cell];
 	const int n = count[cell];
 	// both segment starts are multiples of 32 slots: whole AoSoA blocks line up, copy them double by double
-	const int64_t doubles = ((int64_t)(n + 31) >> 5) << 8;
-	const double* s = src.d + (s0 << 3);
-	double* d = dst.d + (d0 << 3);
-	for (int64_t i = threadIdx.x; i < doubles; i += blockDim.x) d[i] = s[i];
+	// (srcNf == g.nf), or field by field when the copy also widens the layout from 6 to 8 fields
+	if (srcNf == g.nf) {
+		const int64_t doubles = ((int64_t)(n + 31) >> 5) * (32 * g.nf);
+		const double* s = src.d + s0 * g.nf;
+		double* d = dst.d + d0 * g.nf;
+		for (int64_t i = threadIdx.x; i < doubles; i += blockDim.x) d[i] = s[i];
+	} else {
+		for (int64_t e = threadIdx.x; e < (int64_t)n * 8; e += blockDim.x) {
+			const int f = (int)(e & 7);
+			const int64_t slot = e >> 3;
+			dst.d[slot_index(d0 + slot, g.nf) + f * kFieldStride] = f < srcNf ? src.d[slot_index(s0 + slot, srcNf) + f * kFieldStride] : (f == 6 ? srcQ : srcQom);
+		}
+	}
 }
 
 // ---- device self-test of the arithmetic helpers ---------------------------------------------------
@@ -696,42 +715,41 @@ void launch_selftest_division(uint64_t n, uint64_t seed, unsigned long long* bad
 // ---- launchers -----------------------------------------------------------------------------------
 
 // dynamic shared memory of one CTA: the tile stages, and at least the deposit reduction buffer
-static size_t move_smem_bytes(int items, int stages, bool deposit) {
-	(void)deposit;
-	return (size_t)stages * items * kBlock * kFields * sizeof(double);
+static size_t move_smem_bytes(int nf, int stages) {
+	return (size_t)stages * kBlock * nf * sizeof(double);
 }
 
-template<int ITEMS, bool INTERP, bool DEPOSIT, bool MIGRATE, bool PUSH>
+template<int NF, bool INTERP, bool DEPOSIT, bool MIGRATE, bool PUSH>
 static void launch_move_k(const MoveArgs& a, int grid, cudaStream_t st) {
 	static bool configured = false;                  // opt in to > 48 KiB of dynamic shared memory once per instantiation
-	auto kernel = k_move<ITEMS, INTERP, DEPOSIT, MIGRATE, PUSH>;
+	auto kernel = k_move<NF, INTERP, DEPOSIT, MIGRATE, PUSH>;
 	if (!configured) {
-		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)move_smem_bytes(ITEMS, kMaxStages, DEPOSIT));
+		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)move_smem_bytes(NF, kMaxStages));
 		configured = true;
 	}
 	const int stages = std::max(1, std::min(a.stages, kMaxStages));
-	kernel<<<grid, kBlock, move_smem_bytes(ITEMS, stages, DEPOSIT), st>>>(a.g, a.in, a.out, a.cellStart, a.countIn, a.countOut, a.nLeave, a.tag,
-	                                                                     a.fieldEB, a.cellJ, a.stopFlag, a.zBegin, a.zCount, stages);
+	kernel<<<grid, kBlock, move_smem_bytes(NF, stages), st>>>(a.g, a.in, a.out, a.cellStart, a.countIn, a.countOut, a.nLeave, a.tag,
+	                                                          a.fieldEB, a.cellJ, a.stopFlag, a.zBegin, a.zCount, stages);
 }
 
-template<int ITEMS, bool INTERP, bool DEPOSIT>
+template<int NF, bool INTERP, bool DEPOSIT>
 static void launch_move_t(const MoveArgs& a, cudaStream_t st) {
 	const int grid = a.g.nx * a.g.ny * a.zCount;
 	if (grid == 0) return;
-	if (!a.push) { if (DEPOSIT) launch_move_k<ITEMS, false, DEPOSIT, false, false>(a, grid, st); }
-	else if (a.migrate) launch_move_k<ITEMS, INTERP, DEPOSIT, true, true>(a, grid, st);
-	else launch_move_k<ITEMS, INTERP, DEPOSIT, false, true>(a, grid, st);
+	if (!a.push) { if (DEPOSIT) launch_move_k<NF, false, DEPOSIT, false, false>(a, grid, st); }
+	else if (a.migrate) launch_move_k<NF, INTERP, DEPOSIT, true, true>(a, grid, st);
+	else launch_move_k<NF, INTERP, DEPOSIT, false, true>(a, grid, st);
 }
 
-template<int ITEMS>
+template<int NF>
 static void launch_move_i(const MoveArgs& a, cudaStream_t st) {
-	if (a.interpolate) { if (a.deposit) launch_move_t<ITEMS, true, true>(a, st); else launch_move_t<ITEMS, true, false>(a, st); }
-	else { if (a.deposit) launch_move_t<ITEMS, false, true>(a, st); else launch_move_t<ITEMS, false, false>(a, st); }
+	if (a.interpolate) { if (a.deposit) launch_move_t<NF, true, true>(a, st); else launch_move_t<NF, true, false>(a, st); }
+	else { if (a.deposit) launch_move_t<NF, false, true>(a, st); else launch_move_t<NF, false, false>(a, st); }
 }
 
 void launch_move(const MoveArgs& a, cudaStream_t st) {
-	if (a.itemsPerThread >= 2) launch_move_i<2>(a, st);
-	else launch_move_i<1>(a, st);
+	if (a.g.nf == 6) launch_move_i<6>(a, st);
+	else launch_move_i<8>(a, st);
 }
 
 void launch_import(const ImportArgs& a, bool commit, cudaStream_t st) {
@@ -771,8 +789,26 @@ void launch_gather_aos(const Geometry& g, double* aos, const int64_t* aosStart, 
 	k_gather_aos<<<g.nx * g.ny * g.lz, 256, 0, st>>>(g, aos, aosStart, p, cellStart);
 }
 
-void launch_copy_heads(const Geometry& g, const ParticleArrays& src, const int64_t* srcStart, const ParticleArrays& dst, const int64_t* dstStart, const int* count, cudaStream_t st) {
-	k_copy_heads<<<g.nx * g.ny * g.lz, 256, 0, st>>>(g, src, srcStart, dst, dstStart, count);
+void launch_copy_heads(const Geometry& g, const ParticleArrays& src, const int64_t* srcStart, const ParticleArrays& dst, const int64_t* dstStart, const int* count,
+                       int srcNf, double srcQ, double srcQom, cudaStream_t st) {
+	k_copy_heads<<<g.nx * g.ny * g.lz, 256, 0, st>>>(g, src, srcStart, dst, dstStart, count, srcNf, srcQ, srcQom);
+}
+
+// ---- uniform-species test on the staged AoS upload: flag != 0 if any particle's (q, qom) bits differ from the first one's
+__global__ void k_check_species(const double* __restrict__ aos, int64_t n, int* __restrict__ flag) {
+	const long long q0 = __double_as_longlong(aos[6]), m0 = __double_as_longlong(aos[7]);
+	bool differs = false;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+		const double2 v = *reinterpret_cast<const double2*>(aos + i * 8 + 6);
+		differs = differs || __double_as_longlong(v.x) != q0 || __double_as_longlong(v.y) != m0;
+	}
+	if (differs) atomicOr(flag, 1);
+}
+
+void launch_check_species(const double* aos, int64_t n, int* flag, cudaStream_t st) {
+	if (n <= 0) return;
+	const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+	k_check_species<<<grid, 256, 0, st>>>(aos, n, flag);
 }
 
 } // namespace ipic

@@ -16,7 +16,6 @@ struct MoveArgs {
 	double* cellJ;             // cells x 24 corner sums (deposit)
 	const int* stopFlag;
 	int zBegin, zCount;        // owned z-planes [zBegin, zBegin+zCount) of the slab
-	int itemsPerThread;        // particles per thread per tile (1 or 2; tile = items x 128)
 	int stages;                // shared-memory tile stages per CTA (TMA ring)
 	bool interpolate, deposit, migrate, push;   // push=false: deposit-only pass (no write-back)
 };
@@ -43,7 +42,10 @@ void launch_gather_current(const Geometry& g, const double* cellJ, double* J, co
 void launch_count_misplaced(const Geometry& g, const ParticleArrays& p, const int64_t* cellStart, const int* count, unsigned long long* bad, cudaStream_t st);
 void launch_scatter_aos(const Geometry& g, const double* aos, const int64_t* aosStart, const ParticleArrays& p, const int64_t* cellStart, cudaStream_t st);
 void launch_gather_aos(const Geometry& g, double* aos, const int64_t* aosStart, const ParticleArrays& p, const int64_t* cellStart, cudaStream_t st);
-void launch_copy_heads(const Geometry& g, const ParticleArrays& src, const int64_t* srcStart, const ParticleArrays& dst, const int64_t* dstStart, const int* count, cudaStream_t st);
+// copy the live head of every cell into another layout; `g` describes the DESTINATION (its nf), srcNf / srcQ / srcQom the source
+void launch_copy_heads(const Geometry& g, const ParticleArrays& src, const int64_t* srcStart, const ParticleArrays& dst, const int64_t* dstStart, const int* count,
+                       int srcNf, double srcQ, double srcQom, cudaStream_t st);
+void launch_check_species(const double* aos, int64_t n, int* flag, cudaStream_t st);
 
 void launch_selftest_division(uint64_t n, uint64_t seed, unsigned long long* bad, cudaStream_t st);
 

@@ -208,6 +208,7 @@ def run_b200(args):
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0])
     ctx.upload_cells_ptr(counts, host.data_ptr())
+    particle_fields = ctx.particle_fields()
 
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps -------------------
     sampler = ClockSampler(local)
@@ -287,6 +288,7 @@ def run_b200(args):
                                    % (args.grid, args.grid, args.grid, args.particles_per_gpu),
                        "particles": n_total, "particles_per_gpu": args.particles_per_gpu, "grid": [args.grid] * 3,
                        "dt": 0.15, "deposit": not args.no_deposit, "parallelism": "zslab%d" % world,
+                       "particle_fields_in_hbm": particle_fields,
                        "l2": "inputs (%.2f GB of particle state per GPU) are larger than L2; no flush needed" % (n_local * 64 / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "particles_alive_after": alive if world == 1 else None,

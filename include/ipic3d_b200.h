@@ -99,6 +99,14 @@ IPIC_API int  ipic_relayout_count(ipic_ctx* ctx, uint64_t* count);
 IPIC_API int  ipic_comm_unique_id(void* unique_id_128);
 IPIC_API int  ipic_comm_init(ipic_ctx* ctx, const void* unique_id_128);
 
+/* Particle layout in HBM.  When every uploaded particle carries the same (q, qom) bit patterns -- true for all
+ * of the reference's workloads, which run one species -- the context keeps the two constants aside and streams
+ * 6 instead of 8 doubles per particle (96 instead of 128 bytes of HBM traffic per push); downloads, face
+ * messages and results are unaffected.  Slabs agree on the layout before their first step.  enable = 0 forces
+ * the general 8-field layout (takes effect at the next upload).  ipic_particle_fields reports 6 or 8. */
+IPIC_API int  ipic_set_uniform_species(ipic_ctx* ctx, int enable);
+IPIC_API int  ipic_particle_fields(ipic_ctx* ctx, int* fields);
+
 /* Capacity, in particles, of one face message of the z-slab exchange (fixed-size NCCL send/recv per
  * face and step).  0 = automatic: 1/16 of the fuller boundary plane's population, at least 32768; the
  * ranks agree on the maximum at the next step.  Must be called on all ranks alike. */

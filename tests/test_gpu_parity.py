@@ -409,3 +409,67 @@ def test_slabs_exchange_capacity_error():
         with pytest.raises(ipic.IpicError) as e:
             grp.step(2)
         assert e.value.code == -3 and "exchange" in str(e.value)
+
+
+# ---- particle layouts: 6 fields (one species, q/qom kept aside) and the general 8 fields ------------------------
+
+def test_layout_selection():
+    """One species -> 6-field layout; mixed species or ipic_set_uniform_species(0) -> 8 fields; downloads are identical."""
+    import allscale_ipic3d_b200 as ipic
+    if not Ref.available():
+        pytest.skip("oracle/_ref not built")
+    props = Props.make(3, cellWidth=(10.0, 10.0, 10.0), dt=0.15 * 40)
+    r = Ref.uniform_grid(props, 5000)
+    counts, aos = r.counts(), r.particles()
+    o = Oracle(props)
+    o.set_cells(counts, aos)
+    o.step(10)
+    results = []
+    for force_full in (False, True):
+        with ipic.Context(props) as c:
+            if force_full:
+                c.set_uniform_species(False)
+            c.upload_cells(counts, aos)
+            assert c.particle_fields() == (8 if force_full else 6)
+            c.step(10)
+            results.append(c.download_cells())
+    for gc, ga in results:
+        assert np.array_equal(gc, o.counts()) and bits_equal(ga, o.particles())
+    mixed = aos.copy()
+    mixed[::3, 6], mixed[::3, 7] = 1.0, 1.0             # a second species
+    o.set_cells(counts, mixed)
+    o.step(10)
+    with ipic.Context(props) as c:
+        c.upload_cells(counts, mixed)
+        assert c.particle_fields() == 8
+        c.step(10)
+        gc, ga = c.download_cells()
+    assert np.array_equal(gc, o.counts()) and bits_equal(ga, o.particles())
+
+
+def test_slabs_agree_on_layout():
+    """Slabs that each hold ONE species, but different ones, widen to the 8-field layout before the first step; a slab
+    that starts empty adopts its neighbours' species.  Results bit-exact vs the oracle either way."""
+    if not Ref.available():
+        pytest.skip("oracle/_ref not built")
+    props = Props.make(4, cellWidth=(10.0, 10.0, 10.0), dt=0.15 * 40)
+    r = Ref.uniform_grid(props, 20000)
+    counts, aos = r.counts(), r.particles()
+    # (a) species differ between the lower and the upper z-half
+    two = aos.copy()
+    upper = two[:, 2] >= 20.0
+    two[upper, 6], two[upper, 7] = 1.0, 1.0
+    # (b) the upper half starts empty
+    keep = ~upper
+    start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    counts_b = np.array([int(keep[start[i]:start[i + 1]].sum()) for i in range(len(counts))], dtype=np.uint64)
+    for cnt, parts, want_fields in ((counts, two, [8, 8]), (counts_b, aos[keep], [6, 6])):
+        o = Oracle(props)
+        o.set_cells(cnt, parts)
+        o.step(8)
+        with group_for(props, 2) as grp:
+            grp.upload_cells(cnt, parts)
+            grp.step(8)
+            assert grp.particle_fields() == want_fields
+            gc, ga = grp.download_cells()
+        assert np.array_equal(gc, o.counts()) and bits_equal(ga, o.particles())
