@@ -102,6 +102,7 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	__shared__ uint64_t sBar;
 	__shared__ double sRed[DEPOSIT ? 8 * kRedRow : 1];           // deposit reduction: 8 sums x 128 partials per pass
 	__shared__ double sJ[24];                                    // the cell's 8x3 corner sums
+	__shared__ double sGeo[6];                                   // cell origin, cell centre
 
 	const int n = countIn[cell];
 	const int64_t base = cellStart[cell];
@@ -111,6 +112,16 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	const int nTiles = (n + TILE - 1) / TILE;
 
 	if (DEPOSIT && tid < 24) sJ[tid] = 0.0;
+	// geometry of this cell (reference universe_properties.h:125-142), computed once and parked in shared memory:
+	// kept in registers the compiler re-derives it for every tile (int->double conversions included) to stay
+	// under the launch bound, which costs more issue slots than six broadcast LDS
+	if (tid >= 32 && tid < 35) {
+		const int a = tid - 32;
+		const int cc = a == 0 ? cx : (a == 1 ? cy : cz);
+		const double o = g.origin[a] + (double)cc * g.w[a];
+		sGeo[a] = o;
+		sGeo[3 + a] = o + g.hw[a];
+	}
 	if (tid == 0) {
 		for (int s = 0; s < stages; s++) mbar_init(&sFull[s], 1);
 		if (INTERP && PUSH) mbar_init(&sBar, 1);
@@ -142,12 +153,8 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 		}
 	}
 
-	// geometry of this cell (reference universe_properties.h:125-142)
-	double org[3], ctr[3];
-	org[0] = g.origin[0] + (double)cx * g.w[0];
-	org[1] = g.origin[1] + (double)cy * g.w[1];
-	org[2] = g.origin[2] + (double)cz * g.w[2];
-	ctr[0] = org[0] + g.hw[0]; ctr[1] = org[1] + g.hw[1]; ctr[2] = org[2] + g.hw[2];
+	const double* org = sGeo;
+	const double* ctr = sGeo + 3;
 
 	if (INTERP && PUSH && n > 0) mbar_wait(&sBar, 0);
 
@@ -320,7 +327,13 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 // one lives on another GPU, and its outbox is the matching column of the face message received from
 // that GPU (k_face_copy: same entries, same order, AoS payload).
 
-constexpr int kImportBlock = 256;
+#ifndef IPIC_IMPORT_BLOCK
+#define IPIC_IMPORT_BLOCK 256
+#endif
+#ifndef IPIC_IMPORT_MINB
+#define IPIC_IMPORT_MINB 4       // resident CTAs per SM the import is compiled for (B200 sweep: 3 -> 72 us, 4 -> 56 us, 8 -> 68 us)
+#endif
+constexpr int kImportBlock = IPIC_IMPORT_BLOCK;
 constexpr int kImportWarps = kImportBlock / 32;
 
 // outbox entry j of a source: local outboxes grow backwards from the end of the cell's segment,
@@ -348,7 +361,7 @@ struct ImportSource {
 };
 
 template<bool SLAB>
-__global__ void __launch_bounds__(kImportBlock)
+__global__ void __launch_bounds__(kImportBlock, IPIC_IMPORT_MINB)
 k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__ srcStart, const int* __restrict__ srcLeave,
          const unsigned char* __restrict__ tag, const ParticleArrays dst, const int64_t* __restrict__ dstStart,
          const int* __restrict__ stay, int* __restrict__ dstCount, int reserveOwnOutbox, int* __restrict__ stopFlag, int stepIndex, int zBegin, int zCount,
