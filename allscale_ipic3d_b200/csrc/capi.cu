@@ -90,12 +90,14 @@ struct ipic_ctx {
 	ipic_comm* comm = nullptr;
 	std::shared_ptr<ipic_group> group;
 	cudaStream_t commStream = nullptr;
-	cudaEvent_t evPacked = nullptr, evRecv = nullptr, evMoved = nullptr, evJ = nullptr;
+	cudaStream_t bStream = nullptr;                // high priority: movers of the boundary planes + face packing
+	cudaEvent_t evPacked = nullptr, evRecv = nullptr, evMoved = nullptr, evJ = nullptr, evMainReady = nullptr;
 	int64_t userMsgCap = 0;                        // ipic_set_exchange_capacity (0 = automatic)
 	int64_t facePopulation = 0;                    // particles in the fuller of the two boundary planes at upload
 	bool exchangeDirty = true;                     // message capacity must be (re)negotiated before the next step
-	int msgCap = 0;                                // agreed capacity of a face message, in particles
-	size_t msgBytes = 0;
+	int sendCap = 0, recvCap = 0;                  // capacity of the face message buffers, in particles (grown on demand)
+	int* dTotals = nullptr;                        // [0],[1] entries packed into my down / up face; [2],[3] entries coming from below / above
+	int* hTotals = nullptr;                        // pinned mirror
 	char* sendMsg[2] = { nullptr, nullptr };       // [0] face 0 -> slab below, [1] face 1 -> slab above
 	char* recvMsg[2] = { nullptr, nullptr };       // [0] from the slab below, [1] from the slab above
 	int* dFaceCnt = nullptr;
@@ -210,31 +212,31 @@ int drainProfile(ipic_ctx* c) {
 
 // CUDA-event bracket around a group of launches on the context's stream (only while profiling)
 struct ProfSpan {
-	ipic_ctx* c; cudaEvent_t end = nullptr;
-	ProfSpan(ipic_ctx* ctx, int kind) : c(ctx) {
+	ipic_ctx* c; cudaStream_t st; cudaEvent_t end = nullptr;
+	ProfSpan(ipic_ctx* ctx, int kind, cudaStream_t stream = nullptr) : c(ctx), st(stream ? stream : ctx->stream) {
 		if (!c->profiling) return;
 		cudaEvent_t start = nextEvent(c); end = nextEvent(c);
 		c->eventKind.push_back(kind);
-		cudaEventRecord(start, c->stream);
+		cudaEventRecord(start, st);
 	}
-	~ProfSpan() { if (end) cudaEventRecord(end, c->stream); }
+	~ProfSpan() { if (end) cudaEventRecord(end, st); }
 };
 
-FaceMsg faceView(const ipic_ctx* c, char* base) {
+FaceMsg faceView(const ipic_ctx* c, char* base, int cap) {
 	const int nxy = c->g.nx * c->g.ny;
 	FaceMsg m;
 	m.offsets = reinterpret_cast<int*>(base);
 	const size_t offP = (size_t)alignUp((int64_t)(nxy + 1) * 4, 128);
 	m.particles = reinterpret_cast<double*>(base + offP);
-	m.tags = reinterpret_cast<unsigned char*>(base + offP + (size_t)c->msgCap * 64);
-	m.cap = c->msgCap;
+	m.tags = reinterpret_cast<unsigned char*>(base + offP + (size_t)cap * 64);
+	m.cap = cap;
 	return m;
 }
 
 // where the import kernel finds the outboxes of the cells beyond the slab's first / last plane
 void setImportSources(const ipic_ctx* c, ImportArgs& ia) {
 	ia.slab = c->nranks > 1;
-	if (ia.slab) { ia.fromDown = faceView(c, c->recvMsg[0]); ia.fromUp = faceView(c, c->recvMsg[1]); }
+	if (ia.slab) { ia.fromDown = faceView(c, c->recvMsg[0], c->recvCap); ia.fromUp = faceView(c, c->recvMsg[1], c->recvCap); }
 }
 
 // Re-establish a valid layout after the import of `failedStep` ran out of room: the generation that
@@ -365,7 +367,14 @@ int ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, 
 	CK(cudaMalloc(&c->dAosStart, ((size_t)ownedCells(c) + 1) * sizeof(int64_t)));
 	if (nranks > 1) {
 		CK(cudaStreamCreateWithFlags(&c->commStream, cudaStreamNonBlocking));
-		for (cudaEvent_t* e : { &c->evPacked, &c->evRecv, &c->evMoved, &c->evJ }) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+		int prLow = 0, prHigh = 0;
+		CK(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+		CK(cudaStreamCreateWithPriority(&c->bStream, cudaStreamNonBlocking, prHigh));
+		for (cudaEvent_t* e : { &c->evPacked, &c->evRecv, &c->evMoved, &c->evJ, &c->evMainReady }) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+		CK(cudaMalloc(&c->dTotals, 4 * sizeof(int)));
+		CK(cudaMemset(c->dTotals, 0, 4 * sizeof(int)));
+		CK(cudaMallocHost(&c->hTotals, 4 * sizeof(int)));
+		std::memset(c->hTotals, 0, 4 * sizeof(int));
 		CK(cudaMalloc(&c->dFaceCnt, (size_t)2 * g.nx * g.ny * sizeof(int)));
 		CK(cudaMalloc(&c->dNegotiate, (size_t)nranks * 4 * sizeof(int64_t)));
 		CK(cudaMallocHost(&c->hStop, 4 * sizeof(int)));
@@ -382,6 +391,7 @@ int ipic_destroy(ipic_ctx* c) {
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->commStream) cudaStreamSynchronize(c->commStream);
+	if (c->bStream) cudaStreamSynchronize(c->bStream);
 	if (c->comm) comm_destroy(c->comm);
 	if (c->group) {
 		// the remaining members can no longer step; drop the back references
@@ -392,8 +402,11 @@ int ipic_destroy(ipic_ctx* c) {
 	cudaFree(c->dFaceCnt); cudaFree(c->dNegotiate);
 	if (c->hStop) cudaFreeHost(c->hStop);
 	if (c->evStepDone) cudaEventDestroy(c->evStepDone);
-	for (cudaEvent_t e : { c->evPacked, c->evRecv, c->evMoved, c->evJ }) if (e) cudaEventDestroy(e);
+	for (cudaEvent_t e : { c->evPacked, c->evRecv, c->evMoved, c->evJ, c->evMainReady }) if (e) cudaEventDestroy(e);
+	cudaFree(c->dTotals);
+	if (c->hTotals) cudaFreeHost(c->hTotals);
 	if (c->commStream) cudaStreamDestroy(c->commStream);
+	if (c->bStream) cudaStreamDestroy(c->bStream);
 	freeParticleBuffers(c);
 	cudaFree(c->dCellStart); cudaFree(c->dCount); cudaFree(c->dStay); cudaFree(c->dLeave); cudaFree(c->dStop);
 	cudaFree(c->dEB); cudaFree(c->dBext); cudaFree(c->dBc); cudaFree(c->dJ); cudaFree(c->dCellJ);
@@ -661,18 +674,22 @@ int enqueueStepSingle(ipic_ctx* c, const StepFlags& f, int stepIndex) {
 // back to back; an in-process group runs every phase over all members before the next one so that
 // each cross-context event wait refers to an event recorded earlier in host order.
 //
-//   BOUNDARY  mover on the two boundary planes, pack both faces                       [main stream]
-//   EXCHANGE  face messages to / from the z-neighbours (periodic)                     [comm stream]
-//   INTERIOR  mover on the interior planes -- overlaps the exchange                   [main stream]
-//   GATHER_J  all-gather of the slabs' per-cell corner sums -- overlaps the imports     [comm stream]
-//   IMPORT    import interior planes; wait for the exchange; import the boundary planes,
-//             whose out-of-slab neighbours are columns of the received messages       [main stream]
-//   FIELDS    wait for the all-gather; J on every rank; ghost update + field solver   [main stream]
+//   BOUNDARY  movers of the two boundary planes, pack both faces, totals to the host   [boundary stream, high priority]
+//   INTERIOR  mover of the interior planes, concurrently (fills the SMs the boundary
+//             launches leave idle)                                                     [main stream]
+//   SETTLE    host: confirm the previous step (repair a cell overflow), read the packed
+//             totals, swap them with the neighbours, grow message buffers if needed    [host, comm stream]
+//   EXCHANGE  the face messages, exactly as large as their content                     [comm stream]
+//   GATHER_J  all-gather of the slabs' per-cell corner sums -- overlaps the imports    [comm stream]
+//   IMPORT    import of all planes; the out-of-slab neighbours of the boundary planes
+//             are columns of the received messages                                     [main stream]
+//   FIELDS    wait for the all-gather; J on every rank; ghost update + field solver    [main stream]
 //
 // (PRE_DEPOSIT / PRE_GATHER_J: the projection pass of the interpolating mode, which needs J and the
-// field update before the mover.)
+// field update before the mover.)  The host waits (SETTLE) happen while the GPU works through the movers
+// of the same step, which were queued before.
 
-enum SlabPhase { PH_PRE_DEPOSIT, PH_PRE_GATHER_J, PH_BOUNDARY, PH_EXCHANGE, PH_INTERIOR, PH_GATHER_J, PH_IMPORT, PH_FIELDS, PH_COUNT };
+enum SlabPhase { PH_PRE_DEPOSIT, PH_PRE_GATHER_J, PH_BOUNDARY, PH_INTERIOR, PH_SETTLE, PH_EXCHANGE, PH_GATHER_J, PH_IMPORT, PH_FIELDS, PH_COUNT };
 
 size_t faceBytes(const ipic_ctx* c, int64_t cap) {
 	const int nxy = c->g.nx * c->g.ny;
@@ -681,33 +698,39 @@ size_t faceBytes(const ipic_ctx* c, int64_t cap) {
 
 int64_t wantedMsgCap(const ipic_ctx* c) {
 	if (c->userMsgCap > 0) return c->userMsgCap;
-	return std::min<int64_t>(std::max<int64_t>(c->facePopulation / 16, 32768), (int64_t)1 << 26);
+	return std::min<int64_t>(std::max<int64_t>(c->facePopulation / 64, 16384), (int64_t)1 << 26);
+}
+
+int allocFaceBuffers(ipic_ctx* c, char* bufs[2], int64_t cap) {
+	for (int i = 0; i < 2; i++) {
+		cudaFree(bufs[i]);
+		bufs[i] = nullptr;
+		CK(cudaMalloc(&bufs[i], faceBytes(c, cap)));
+		CK(cudaMemset(bufs[i], 0, faceBytes(c, cap)));
+	}
+	return IPIC_OK;
 }
 
 int allocExchange(ipic_ctx* c, int64_t cap) {
 	CK(cudaSetDevice(c->device));
 	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaStreamSynchronize(c->bStream));
 	CK(cudaStreamSynchronize(c->commStream));
-	for (int i = 0; i < 2; i++) { cudaFree(c->sendMsg[i]); cudaFree(c->recvMsg[i]); c->sendMsg[i] = c->recvMsg[i] = nullptr; }
-	c->msgCap = (int)cap;
-	c->msgBytes = faceBytes(c, cap);
-	for (int i = 0; i < 2; i++) {
-		CK(cudaMalloc(&c->sendMsg[i], c->msgBytes));
-		CK(cudaMalloc(&c->recvMsg[i], c->msgBytes));
-		CK(cudaMemset(c->sendMsg[i], 0, c->msgBytes));
-		CK(cudaMemset(c->recvMsg[i], 0, c->msgBytes));
-	}
+	int rc = allocFaceBuffers(c, c->sendMsg, cap);
+	if (rc) return rc;
+	rc = allocFaceBuffers(c, c->recvMsg, cap);
+	if (rc) return rc;
+	c->sendCap = c->recvCap = (int)cap;
 	c->exchangeDirty = false;
 	return IPIC_OK;
 }
 
-// What a slab contributes to the negotiation before the first step after an upload: the face-message capacity
-// it wants, and its species state (0 = no particles, 6 = one species with the (q, qom) bits that follow, 8 = mixed).
-struct SlabOffer { int64_t cap, species, qBits, qomBits; };
+// What a slab contributes to the negotiation before the first step after an upload: its species state
+// (0 = no particles, 6 = one species with the (q, qom) bits that follow, 8 = mixed).
+struct SlabOffer { int64_t species, qBits, qomBits, pad; };
 
 SlabOffer offerOf(const ipic_ctx* c) {
-	SlabOffer o;
-	o.cap = wantedMsgCap(c);
+	SlabOffer o{};
 	o.species = c->emptyUpload ? 0 : c->g.nf;
 	std::memcpy(&o.qBits, &c->g.uq, 8);
 	std::memcpy(&o.qomBits, &c->g.uqom, 8);
@@ -734,7 +757,8 @@ int agreeOnLayout(ipic_ctx* c, const std::vector<SlabOffer>& all) {
 	return IPIC_OK;
 }
 
-// all ranks agree on max(wanted capacity) and on the layout; NCCL contexts must all enter this in the same ipic_step call
+// before the first step after an upload: agree on the layout, set up the message buffers.  NCCL contexts must
+// all enter this in the same ipic_step call.
 int negotiateExchangeNccl(ipic_ctx* c) {
 	if (!c->exchangeDirty) return IPIC_OK;
 	CK(cudaSetDevice(c->device));
@@ -746,23 +770,20 @@ int negotiateExchangeNccl(ipic_ctx* c) {
 	if (rc) return rc;
 	CK(cudaMemcpyAsync(all.data(), d, all.size() * sizeof(SlabOffer), cudaMemcpyDeviceToHost, c->commStream));
 	CK(cudaStreamSynchronize(c->commStream));
-	int64_t cap = 0;
-	for (const SlabOffer& o : all) cap = std::max(cap, o.cap);
 	rc = agreeOnLayout(c, all);
 	if (rc) return rc;
-	return allocExchange(c, cap);
+	return allocExchange(c, wantedMsgCap(c));
 }
 
 int negotiateExchangeGroup(ipic_group* grp) {
 	bool dirty = false;
 	std::vector<SlabOffer> all;
-	int64_t cap = 0;
-	for (ipic_ctx* m : grp->members) { dirty = dirty || m->exchangeDirty; all.push_back(offerOf(m)); cap = std::max(cap, all.back().cap); }
+	for (ipic_ctx* m : grp->members) { dirty = dirty || m->exchangeDirty; all.push_back(offerOf(m)); }
 	if (!dirty) return IPIC_OK;
 	for (ipic_ctx* m : grp->members) {
 		int rc = agreeOnLayout(m, all);
 		if (rc) return rc;
-		rc = allocExchange(m, cap);
+		rc = allocExchange(m, wantedMsgCap(m));
 		if (rc) return rc;
 	}
 	return IPIC_OK;
@@ -777,6 +798,7 @@ ipic_ctx* neighbour(const ipic_ctx* c, int dir) {      // in-process group only
 int allGatherCellJ(ipic_ctx* c) {
 	const size_t slabDoubles = (size_t)c->g.nx * c->g.ny * c->g.lz * 24;
 	CK(cudaStreamWaitEvent(c->commStream, c->evMoved, 0));
+	CK(cudaStreamWaitEvent(c->commStream, c->evPacked, 0));
 	if (c->comm) {
 		int rc = comm_allgather(c->comm, c->dCellJ + (size_t)c->rank * slabDoubles, c->dCellJ, slabDoubles * sizeof(double), c->commStream, g_lastError);
 		if (rc) return rc;
@@ -784,6 +806,7 @@ int allGatherCellJ(ipic_ctx* c) {
 		for (ipic_ctx* m : c->group->members) {
 			if (m == c) continue;
 			CK(cudaStreamWaitEvent(c->commStream, m->evMoved, 0));
+			CK(cudaStreamWaitEvent(c->commStream, m->evPacked, 0));
 			CK(cudaMemcpyPeerAsync(c->dCellJ + (size_t)m->rank * slabDoubles, c->device, m->dCellJ + (size_t)m->rank * slabDoubles, m->device,
 			                       slabDoubles * sizeof(double), c->commStream));
 		}
@@ -807,16 +830,37 @@ int waitPeersDoneWithCellJ(ipic_ctx* c) {
 	return IPIC_OK;
 }
 
+// pack both faces of generation `out` into the send buffers and report the totals to the host (boundary stream)
+int packFaces(ipic_ctx* c, int stepIndex) {
+	const int out = c->cur ^ 1;
+	launch_face_pack(c->g, c->buf[out], c->dCellStart, c->dLeave, c->dTag, c->dFaceCnt, faceView(c, c->sendMsg[0], c->sendCap),
+	                 faceView(c, c->sendMsg[1], c->sendCap), c->dTotals, c->dStop, stepIndex, c->bStream);
+	c->launches += 3;
+	CK(cudaMemcpyAsync(c->hTotals, c->dTotals, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->bStream));
+	return IPIC_OK;
+}
+
+// the pieces of one face message that actually hold data: column offsets, `total` particle records, `total` tags
+struct FacePieces { void* p[3]; size_t bytes[3]; };
+FacePieces piecesOf(const ipic_ctx* c, char* base, int cap, int total) {
+	const FaceMsg m = faceView(c, base, cap);
+	FacePieces f;
+	f.p[0] = m.offsets;   f.bytes[0] = (size_t)(c->g.nx * c->g.ny + 1) * sizeof(int);
+	f.p[1] = m.particles; f.bytes[1] = (size_t)total * 64;
+	f.p[2] = m.tags;      f.bytes[2] = (size_t)total;
+	return f;
+}
+
 int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 	CK(cudaSetDevice(c->device));
 	const int lz = c->g.lz;
-	const int out = c->cur ^ 1;
 	switch (phase) {
 	case PH_PRE_DEPOSIT:
 		if (!(f.project && f.interp)) break;
 		{ int rc = waitPeersDoneWithCellJ(c); if (rc) return rc; }
 		depositPass(c, f, 0, lz);
 		CK(cudaEventRecord(c->evMoved, c->stream));
+		CK(cudaEventRecord(c->evPacked, c->stream));          // the all-gather waits for both events; nothing runs on the boundary stream here
 		break;
 	case PH_PRE_GATHER_J:
 		if (!(f.project && f.interp)) break;
@@ -826,41 +870,24 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 	case PH_BOUNDARY: {
 		if (!f.fuseDeposit) fieldPhase(c, f);
 		if (f.fuseDeposit) { int rc = waitPeersDoneWithCellJ(c); if (rc) return rc; }
+		// everything queued on the main stream so far (previous imports, field phase) comes first
+		CK(cudaEventRecord(c->evMainReady, c->stream));
+		CK(cudaStreamWaitEvent(c->bStream, c->evMainReady, 0));
 		if (c->group && f.migrate) {
 			// the neighbours pulled last step's messages out of my send buffers on their comm streams
-			CK(cudaStreamWaitEvent(c->stream, neighbour(c, -1)->evRecv, 0));
-			CK(cudaStreamWaitEvent(c->stream, neighbour(c, +1)->evRecv, 0));
+			CK(cudaStreamWaitEvent(c->bStream, neighbour(c, -1)->evRecv, 0));
+			CK(cudaStreamWaitEvent(c->bStream, neighbour(c, +1)->evRecv, 0));
 		}
 		{
-			ProfSpan span(c, 0);
-			launch_move(moveArgs(c, f, 0, 1), c->stream);
+			ProfSpan span(c, 0, c->bStream);
+			launch_move(moveArgs(c, f, 0, 1), c->bStream);
 			c->launches++;
-			if (lz > 1) { launch_move(moveArgs(c, f, lz - 1, 1), c->stream); c->launches++; }
+			if (lz > 1) { launch_move(moveArgs(c, f, lz - 1, 1), c->bStream); c->launches++; }
 		}
-		if (f.migrate) {
-			launch_face_pack(c->g, c->buf[out], c->dCellStart, c->dLeave, c->dTag, c->dFaceCnt, faceView(c, c->sendMsg[0]), faceView(c, c->sendMsg[1]),
-			                 c->dStop, stepIndex, c->stream);
-			c->launches += 3;
-			CK(cudaEventRecord(c->evPacked, c->stream));
-		}
+		if (f.migrate) { int rc = packFaces(c, stepIndex); if (rc) return rc; }
+		CK(cudaEventRecord(c->evPacked, c->bStream));
 		break;
 	}
-	case PH_EXCHANGE:
-		if (!f.migrate) break;
-		CK(cudaStreamWaitEvent(c->commStream, c->evPacked, 0));
-		if (c->comm) {
-			int rc = comm_exchange(c->comm, c->sendMsg[1], c->recvMsg[0], c->sendMsg[0], c->recvMsg[1], c->msgBytes, c->commStream, g_lastError);
-			if (rc) return rc;
-		} else {
-			ipic_ctx* down = neighbour(c, -1);
-			ipic_ctx* up = neighbour(c, +1);
-			CK(cudaStreamWaitEvent(c->commStream, down->evPacked, 0));
-			CK(cudaStreamWaitEvent(c->commStream, up->evPacked, 0));
-			CK(cudaMemcpyPeerAsync(c->recvMsg[0], c->device, down->sendMsg[1], down->device, c->msgBytes, c->commStream));
-			CK(cudaMemcpyPeerAsync(c->recvMsg[1], c->device, up->sendMsg[0], up->device, c->msgBytes, c->commStream));
-		}
-		CK(cudaEventRecord(c->evRecv, c->commStream));
-		break;
 	case PH_INTERIOR:
 		if (lz > 2) {
 			ProfSpan span(c, 0);
@@ -869,16 +896,40 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 		}
 		if (f.fuseDeposit) CK(cudaEventRecord(c->evMoved, c->stream));
 		break;
+	case PH_EXCHANGE: {
+		if (!f.migrate) break;
+		const int* t = c->hTotals;                            // settled: [0] my down face, [1] my up face, [2] from below, [3] from above
+		const FacePieces sUp = piecesOf(c, c->sendMsg[1], c->sendCap, t[1]), sDown = piecesOf(c, c->sendMsg[0], c->sendCap, t[0]);
+		const FacePieces rDown = piecesOf(c, c->recvMsg[0], c->recvCap, t[2]), rUp = piecesOf(c, c->recvMsg[1], c->recvCap, t[3]);
+		CK(cudaStreamWaitEvent(c->commStream, c->evPacked, 0));
+		if (c->comm) {
+			CommPiece sends[6], recvs[6];
+			for (int k = 0; k < 3; k++) {
+				sends[k] = { sUp.p[k], sUp.bytes[k], +1 };   sends[3 + k] = { sDown.p[k], sDown.bytes[k], -1 };
+				recvs[k] = { rDown.p[k], rDown.bytes[k], -1 }; recvs[3 + k] = { rUp.p[k], rUp.bytes[k], +1 };
+			}
+			int rc = comm_sendrecv(c->comm, sends, 6, recvs, 6, c->commStream, g_lastError);
+			if (rc) return rc;
+		} else {
+			ipic_ctx* down = neighbour(c, -1);
+			ipic_ctx* up = neighbour(c, +1);
+			CK(cudaStreamWaitEvent(c->commStream, down->evPacked, 0));
+			CK(cudaStreamWaitEvent(c->commStream, up->evPacked, 0));
+			const FacePieces fromDown = piecesOf(down, down->sendMsg[1], down->sendCap, t[2]), fromUp = piecesOf(up, up->sendMsg[0], up->sendCap, t[3]);
+			for (int k = 0; k < 3; k++) {
+				if (rDown.bytes[k]) CK(cudaMemcpyPeerAsync(rDown.p[k], c->device, fromDown.p[k], down->device, rDown.bytes[k], c->commStream));
+				if (rUp.bytes[k]) CK(cudaMemcpyPeerAsync(rUp.p[k], c->device, fromUp.p[k], up->device, rUp.bytes[k], c->commStream));
+			}
+		}
+		CK(cudaEventRecord(c->evRecv, c->commStream));
+		break;
+	}
 	case PH_GATHER_J:
 		if (!f.fuseDeposit) break;
 		{ int rc = allGatherCellJ(c); if (rc) return rc; }      // on the comm stream, under the imports
 		break;
-	case PH_FIELDS:
-		if (!f.fuseDeposit) break;
-		{ int rc = finishCurrent(c); if (rc) return rc; }
-		fieldPhase(c, f);
-		break;
 	case PH_IMPORT:
+		CK(cudaStreamWaitEvent(c->stream, c->evPacked, 0));   // the boundary planes' movers
 		if (f.migrate) {
 			{
 				ProfSpan span(c, 1);
@@ -894,16 +945,18 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 		c->cur ^= 1;
 		CK(cudaGetLastError());
 		break;
+	case PH_FIELDS:
+		if (!f.fuseDeposit) break;
+		{ int rc = finishCurrent(c); if (rc) return rc; }
+		fieldPhase(c, f);
+		break;
 	default: break;
 	}
 	return IPIC_OK;
 }
 
 int enqueueStep(ipic_ctx* c, uint32_t flags, int stepIndex) {
-	const StepFlags f(flags);
-	if (c->nranks == 1) return enqueueStepSingle(c, f, stepIndex);
-	for (int ph = 0; ph < PH_COUNT; ph++) { int rc = slabPhase(c, ph, f, stepIndex); if (rc) return rc; }
-	return IPIC_OK;
+	return enqueueStepSingle(c, StepFlags(flags), stepIndex);      // slab contexts are driven by runSlabSteps
 }
 
 int enqueueSteps(ipic_ctx* c, uint64_t first, uint64_t count, uint32_t flags) {
@@ -915,15 +968,14 @@ int enqueueSteps(ipic_ctx* c, uint64_t first, uint64_t count, uint32_t flags) {
 }
 
 int stopError(ipic_ctx* c, const int* stop) {
-	if (stop[3] == 1) return fail(IPIC_ERR_CAPACITY, "rank %d: more than %d particles cross a slab face in step %d: raise ipic_set_exchange_capacity", c->rank, c->msgCap, stop[1]);
-	if (stop[3] == 2) return fail(IPIC_ERR_CAPACITY, "rank %d: unusable face message received in step %d (the sending rank ran out of message space: raise ipic_set_exchange_capacity)", c->rank, stop[1]);
-	return fail(IPIC_ERR_CAPACITY, "rank %d: cell segment overflow in a multi-GPU run (step %d): raise the head-room with ipic_set_headroom", c->rank, stop[1]);
+	if (stop[3] == 2) return fail(IPIC_ERR_INTERNAL, "rank %d: unusable face message received in step %d", c->rank, stop[1]);
+	return fail(IPIC_ERR_CAPACITY, "rank %d: cell segment overflow in a multi-GPU run (step %d) could not be repaired", c->rank, stop[1]);
 }
 
 // Did the slab step whose PH_IMPORT was enqueued last complete without overflowing a cell segment?  If it
 // did overflow: the generation being written still holds every stayer and every outbox, and the received
-// face messages are untouched, so this rank re-layouts on its own and redoes that import; nothing of the NEXT step has left
-// this GPU yet (see runSlabSteps), so the other ranks never see the hiccup.
+// face messages are untouched, so this rank re-layouts on its own and redoes that import; nothing of the
+// NEXT step has left this GPU yet (see runSlabSteps), so the other ranks never see the hiccup.
 int confirmSlabStep(ipic_ctx* c, bool* recovered) {
 	*recovered = false;
 	CK(cudaSetDevice(c->device));
@@ -932,6 +984,7 @@ int confirmSlabStep(ipic_ctx* c, bool* recovered) {
 	if (c->hStop[3]) return stopError(c, c->hStop);
 	const int failed = c->hStop[1];
 	CK(cudaStreamSynchronize(c->stream));                    // drain the (skipped) launches queued behind the failure
+	CK(cudaStreamSynchronize(c->bStream));
 	int rc = relayoutAfterOverflow(c, c->cur, failed);
 	if (rc) return rc;
 	c->relayouts++;
@@ -939,10 +992,52 @@ int confirmSlabStep(ipic_ctx* c, bool* recovered) {
 	return IPIC_OK;
 }
 
+// SETTLE, part 1: my packed totals are on the host; a face that does not fit its buffer gets a bigger one and is packed again
+int settleSendSizes(ipic_ctx* c, int stepIndex) {
+	CK(cudaSetDevice(c->device));
+	CK(cudaEventSynchronize(c->evPacked));
+	const int need = std::max(c->hTotals[0], c->hTotals[1]);
+	if (need <= c->sendCap) return IPIC_OK;
+	const int64_t cap = alignUp((int64_t)need + need / 2 + 1024, 1024);
+	if (c->userMsgCap > 0) return fail(IPIC_ERR_CAPACITY, "rank %d: %d particles cross a slab face in step %d, exchange capacity fixed at %lld by ipic_set_exchange_capacity",
+	                                   c->rank, need, stepIndex, (long long)c->userMsgCap);
+	CK(cudaStreamSynchronize(c->commStream));               // nobody reads the old buffers any more (previous step confirmed)
+	int rc = allocFaceBuffers(c, c->sendMsg, cap);
+	if (rc) return rc;
+	c->sendCap = (int)cap;
+	rc = packFaces(c, stepIndex);
+	if (rc) return rc;
+	CK(cudaEventRecord(c->evPacked, c->bStream));
+	CK(cudaEventSynchronize(c->evPacked));
+	return IPIC_OK;
+}
+
+// SETTLE, part 2 (NCCL): swap totals with the z-neighbours; part 3: make room for what is coming
+int settleRecvSizesNccl(ipic_ctx* c) {
+	CommPiece sends[2] = { { c->dTotals + 1, sizeof(int), +1 }, { c->dTotals + 0, sizeof(int), -1 } };
+	CommPiece recvs[2] = { { c->dTotals + 2, sizeof(int), -1 }, { c->dTotals + 3, sizeof(int), +1 } };
+	int rc = comm_sendrecv(c->comm, sends, 2, recvs, 2, c->commStream, g_lastError);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(c->hTotals + 2, c->dTotals + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->commStream));
+	CK(cudaStreamSynchronize(c->commStream));
+	return IPIC_OK;
+}
+
+int growRecvBuffers(ipic_ctx* c) {
+	const int need = std::max(c->hTotals[2], c->hTotals[3]);
+	if (need <= c->recvCap) return IPIC_OK;
+	CK(cudaSetDevice(c->device));
+	const int64_t cap = alignUp((int64_t)need + need / 2 + 1024, 1024);
+	int rc = allocFaceBuffers(c, c->recvMsg, cap);         // the previous step (its imports read the old buffers) is confirmed
+	if (rc) return rc;
+	c->recvCap = (int)cap;
+	return IPIC_OK;
+}
+
 bool phaseCommunicates(int ph, const StepFlags& f) {
 	switch (ph) {
 	case PH_PRE_GATHER_J: return f.project && f.interp;
-	case PH_EXCHANGE: return f.migrate;
+	case PH_SETTLE: return f.migrate;
 	case PH_GATHER_J: return f.fuseDeposit;
 	default: return false;
 	}
@@ -951,7 +1046,7 @@ bool phaseCommunicates(int ph, const StepFlags& f) {
 // Steps of slab contexts (one NCCL rank, or all members of an in-process group).  The host runs at most
 // one step ahead of the device: before the first communication of step s is enqueued, step s-1 is
 // confirmed (and repaired if a cell segment overflowed).  The launches of step s queued before that
-// point (boundary movers + pack, or the projection pass) keep the GPU busy meanwhile.
+// point (all movers + pack, or the projection pass) keep the GPU busy meanwhile.
 int runSlabSteps(ipic_ctx** ctxs, int n, uint64_t numSteps, uint32_t flags, double* tFirst, double* tRest) {
 	const StepFlags f(flags);
 	std::vector<cudaEvent_t> ev((size_t)n * 3);
@@ -970,6 +1065,17 @@ int runSlabSteps(ipic_ctx** ctxs, int n, uint64_t numSteps, uint32_t flags, doub
 		}
 		return IPIC_OK;
 	};
+	auto settle = [&](int stepIndex) -> int {
+		for (int r = 0; r < n; r++) { int rc = settleSendSizes(ctxs[r], stepIndex); if (rc) return rc; }
+		for (int r = 0; r < n; r++) {
+			ipic_ctx* c = ctxs[r];
+			if (c->comm) { int rc = settleRecvSizesNccl(c); if (rc) return rc; }
+			else { c->hTotals[2] = neighbour(c, -1)->hTotals[1]; c->hTotals[3] = neighbour(c, +1)->hTotals[0]; }
+			int rc = growRecvBuffers(c);
+			if (rc) return rc;
+		}
+		return IPIC_OK;
+	};
 	for (uint64_t s = 0; s < numSteps; s++) {
 		const int stepIndex = (int)std::min<uint64_t>(s, 0x7ffffff0u);
 		bool confirmed = s == 0;
@@ -978,6 +1084,10 @@ int runSlabSteps(ipic_ctx** ctxs, int n, uint64_t numSteps, uint32_t flags, doub
 				int rc = confirmAll(stepIndex, ph);
 				if (rc) return rc;
 				confirmed = true;
+			}
+			if (ph == PH_SETTLE) {
+				if (f.migrate) { int rc = settle(stepIndex); if (rc) return rc; }
+				continue;
 			}
 			for (int r = 0; r < n; r++) { int rc = slabPhase(ctxs[r], ph, f, stepIndex); if (rc) return rc; }
 		}
@@ -996,6 +1106,7 @@ int runSlabSteps(ipic_ctx** ctxs, int n, uint64_t numSteps, uint32_t flags, doub
 		CK(cudaSetDevice(c->device));
 		CK(cudaEventRecord(ev[(size_t)r * 3 + 2], c->stream));
 		CK(cudaStreamSynchronize(c->stream));
+		CK(cudaStreamSynchronize(c->bStream));
 		CK(cudaStreamSynchronize(c->commStream));
 		float a = 0, b = 0;
 		CK(cudaEventElapsedTime(&a, ev[(size_t)r * 3], ev[(size_t)r * 3 + 1]));

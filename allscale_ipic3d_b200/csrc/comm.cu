@@ -81,15 +81,13 @@ void comm_destroy(ipic_comm* c) {
 	delete c;
 }
 
-int comm_exchange(ipic_comm* c, const void* sendUp, void* recvFromDown, const void* sendDown, void* recvFromUp, size_t bytes, cudaStream_t st, std::string& err) {
+int comm_sendrecv(ipic_comm* c, const CommPiece* sends, int nSends, const CommPiece* recvs, int nRecvs, cudaStream_t st, std::string& err) {
 	NcclApi* a = api(err);
 	if (!a || !c) { if (a) err = "no communicator"; return IPIC_ERR_COMM; }
 	const int up = (c->rank + 1) % c->nranks, down = (c->rank + c->nranks - 1) % c->nranks;
 	NC(a->GroupStart());
-	NC(a->Send(sendUp, bytes, ncclInt8, up, c->comm, st));
-	NC(a->Send(sendDown, bytes, ncclInt8, down, c->comm, st));
-	NC(a->Recv(recvFromDown, bytes, ncclInt8, down, c->comm, st));
-	NC(a->Recv(recvFromUp, bytes, ncclInt8, up, c->comm, st));
+	for (int i = 0; i < nSends; i++) if (sends[i].bytes) NC(a->Send(sends[i].p, sends[i].bytes, ncclInt8, sends[i].dir > 0 ? up : down, c->comm, st));
+	for (int i = 0; i < nRecvs; i++) if (recvs[i].bytes) NC(a->Recv(recvs[i].p, recvs[i].bytes, ncclInt8, recvs[i].dir > 0 ? up : down, c->comm, st));
 	NC(a->GroupEnd());
 	return IPIC_OK;
 }

@@ -10,7 +10,11 @@ struct ipic_comm;
 int comm_unique_id(void* id128, std::string& err);
 int comm_create(ipic_comm** out, const void* id128, int rank, int nranks, std::string& err);
 void comm_destroy(ipic_comm* c);
-// exchange `bytes` with both z-neighbours: sendUp -> rank+1, sendDown -> rank-1 (periodic), receive likewise
-int comm_exchange(ipic_comm* c, const void* sendUp, void* recvFromDown, const void* sendDown, void* recvFromUp, size_t bytes, cudaStream_t st, std::string& err);
+// one piece of a z-neighbour exchange: `dir` +1 = the slab above (rank+1), -1 = the slab below (rank-1), periodic
+struct CommPiece { void* p; size_t bytes; int dir; };
+// all sends and receives in ONE NCCL group; pieces of zero bytes are skipped (both sides know the sizes).  With two
+// ranks both neighbours are the same peer: NCCL matches the pieces per peer in the order given, so everybody lists
+// sends as [to above..., to below...] and receives as [from below..., from above...].
+int comm_sendrecv(ipic_comm* c, const CommPiece* sends, int nSends, const CommPiece* recvs, int nRecvs, cudaStream_t st, std::string& err);
 // all-gather equally sized pieces in rank order
 int comm_allgather(ipic_comm* c, const void* send, void* recv, size_t bytesPerRank, cudaStream_t st, std::string& err);

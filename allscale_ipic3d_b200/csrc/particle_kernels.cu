@@ -530,7 +530,7 @@ k_face_count(const Geometry g, const int64_t* __restrict__ cellStart, const int*
 
 // one CTA of 1024 threads per face: exclusive scan of the column counts into the message header
 __global__ void __launch_bounds__(1024)
-k_face_scan(const Geometry g, const int* __restrict__ faceCnt, FaceMsg m0, FaceMsg m1, int* __restrict__ stopFlag, int stepIndex) {
+k_face_scan(const Geometry g, const int* __restrict__ faceCnt, FaceMsg m0, FaceMsg m1, int* __restrict__ totals) {
 	__shared__ int sWarp[32];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int nxy = g.nx * g.ny;
@@ -558,7 +558,7 @@ k_face_scan(const Geometry g, const int* __restrict__ faceCnt, FaceMsg m0, FaceM
 	}
 	if (tid == 0) {
 		m.offsets[nxy] = carry;
-		if (carry > m.cap) { atomicMin(stopFlag + 1, stepIndex); atomicExch(stopFlag + 3, 1); atomicExch(stopFlag, 1); }
+		totals[blockIdx.x] = carry;          // the host compares it with the buffer capacity and packs again into a bigger one if needed
 	}
 }
 
@@ -777,11 +777,12 @@ void launch_import(const ImportArgs& a, bool commit, cudaStream_t st) {
 }
 
 void launch_face_pack(const Geometry& g, const ParticleArrays& src, const int64_t* cellStart, const int* nLeave, const unsigned char* tag,
-                      int* faceCnt, const FaceMsg& down, const FaceMsg& up, int* stopFlag, int stepIndex, cudaStream_t st) {
+                      int* faceCnt, const FaceMsg& down, const FaceMsg& up, int* totals, int* stopFlag, int stepIndex, cudaStream_t st) {
+	(void)stepIndex;
 	const int tasks = 2 * g.nx * g.ny;
 	const int grid = (tasks + kFaceWarps - 1) / kFaceWarps;
 	k_face_count<<<grid, kFaceBlock, 0, st>>>(g, cellStart, nLeave, tag, faceCnt, stopFlag);
-	k_face_scan<<<2, 1024, 0, st>>>(g, faceCnt, down, up, stopFlag, stepIndex);
+	k_face_scan<<<2, 1024, 0, st>>>(g, faceCnt, down, up, totals);
 	k_face_copy<<<grid, kFaceBlock, 0, st>>>(g, src, cellStart, nLeave, tag, down, up);
 }
 

@@ -37,7 +37,7 @@ void launch_move(const MoveArgs& a, cudaStream_t st);
 void launch_import(const ImportArgs& a, bool commit, cudaStream_t st);
 // z-slab exchange: pack both faces of the slab into their messages (3 launches)
 void launch_face_pack(const Geometry& g, const ParticleArrays& src, const int64_t* cellStart, const int* nLeave, const unsigned char* tag,
-                      int* faceCnt, const FaceMsg& down, const FaceMsg& up, int* stopFlag, int stepIndex, cudaStream_t st);
+                      int* faceCnt, const FaceMsg& down, const FaceMsg& up, int* totals, int* stopFlag, int stepIndex, cudaStream_t st);
 void launch_gather_current(const Geometry& g, const double* cellJ, double* J, const int* stopFlag, cudaStream_t st);
 void launch_count_misplaced(const Geometry& g, const ParticleArrays& p, const int64_t* cellStart, const int* count, unsigned long long* bad, cudaStream_t st);
 void launch_scatter_aos(const Geometry& g, const double* aos, const int64_t* aosStart, const ParticleArrays& p, const int64_t* cellStart, cudaStream_t st);

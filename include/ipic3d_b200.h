@@ -107,9 +107,9 @@ IPIC_API int  ipic_comm_init(ipic_ctx* ctx, const void* unique_id_128);
 IPIC_API int  ipic_set_uniform_species(ipic_ctx* ctx, int enable);
 IPIC_API int  ipic_particle_fields(ipic_ctx* ctx, int* fields);
 
-/* Capacity, in particles, of one face message of the z-slab exchange (fixed-size NCCL send/recv per
- * face and step).  0 = automatic: 1/16 of the fuller boundary plane's population, at least 32768; the
- * ranks agree on the maximum at the next step.  Must be called on all ranks alike. */
+/* Face messages of the z-slab exchange are sent exactly as large as their content (the host reads the packed
+ * totals while the movers of the same step run) and their buffers grow on demand.  particles > 0 pins the
+ * buffer capacity instead (a step that needs more fails with IPIC_ERR_CAPACITY); 0 = automatic (default). */
 IPIC_API int  ipic_set_exchange_capacity(ipic_ctx* ctx, int64_t particles);
 
 /* Single-process multi-GPU: ndev slab contexts (rank r on devices[r]; devices may repeat) that exchange
