@@ -21,7 +21,7 @@ API_SYMBOLS = [
     "ipic_cell_counts", "ipic_total_particles", "ipic_upload_fields", "ipic_download_fields", "ipic_step",
     "ipic_step_async", "ipic_sync", "ipic_count_misplaced", "ipic_profile_reset", "ipic_profile_get", "ipic_selftest",
     "ipic_set_exchange_capacity", "ipic_group_create", "ipic_group_step", "ipic_relayout_count",
-    "ipic_alloc_pinned", "ipic_free_pinned", "ipic_set_uniform_species", "ipic_particle_fields",
+    "ipic_alloc_pinned", "ipic_free_pinned", "ipic_set_uniform_species", "ipic_particle_fields", "ipic_profile_phases",
 ]
 
 
@@ -232,6 +232,11 @@ class Context:
 
     def profile_reset(self):
         self._ck(self.lib.ipic_profile_reset(self.h))
+
+    def profile_phases(self):
+        out = (C.c_double * 4)()
+        self._ck(self.lib.ipic_profile_phases(self.h, out))
+        return list(out)
 
     def profile_get(self):
         a, b, n = C.c_double(0), C.c_double(0), C.c_uint64(0)

@@ -83,6 +83,7 @@ struct ipic_ctx {
 	std::vector<int> eventKind;                    // per pair: 0 mover, 1 import
 	size_t eventsUsed = 0;
 	double moverMs = 0, importMs = 0;
+	double phaseMs[4] = { 0, 0, 0, 0 };             // slab steps: [0] movers (span), [1] imports, [2] waiting for the exchange, [3] waiting for J + field phase
 	uint64_t launches = 0;
 	uint64_t relayouts = 0;                        // cell-segment overflows repaired so far
 
@@ -98,6 +99,7 @@ struct ipic_ctx {
 	int sendCap = 0, recvCap = 0;                  // capacity of the face message buffers, in particles (grown on demand)
 	int* dTotals = nullptr;                        // [0],[1] entries packed into my down / up face; [2],[3] entries coming from below / above
 	int* hTotals = nullptr;                        // pinned mirror
+	cudaEvent_t moverSpanEnd = nullptr;            // profiling: pending end of the movers' span
 	char* sendMsg[2] = { nullptr, nullptr };       // [0] face 0 -> slab below, [1] face 1 -> slab above
 	char* recvMsg[2] = { nullptr, nullptr };       // [0] from the slab below, [1] from the slab above
 	int* dFaceCnt = nullptr;
@@ -202,8 +204,11 @@ cudaEvent_t nextEvent(ipic_ctx* c) {
 int drainProfile(ipic_ctx* c) {
 	for (size_t i = 0; i + 1 < c->eventsUsed; i += 2) {
 		float a = 0;
-		CK(cudaEventElapsedTime(&a, c->events[i], c->events[i + 1]));
-		(c->eventKind[i / 2] == 0 ? c->moverMs : c->importMs) += a;
+		if (cudaEventElapsedTime(&a, c->events[i], c->events[i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }   // a span cut short by a repair
+		const int kind = c->eventKind[i / 2];
+		if (kind == 0) c->moverMs += a;
+		if (kind == 1) c->importMs += a;
+		c->phaseMs[kind & 3] += a;
 	}
 	c->eventsUsed = 0;
 	c->eventKind.clear();
@@ -639,6 +644,20 @@ void importPlanes(ipic_ctx* c, int stepIndex, int zBegin, int zCount, bool commi
 	c->launches += commit ? 2 : 1;
 }
 
+// event pair whose two halves are recorded in different phases (slab steps: the span of all movers)
+void spanBegin(ipic_ctx* c, int kind, cudaEvent_t* pendingEnd) {
+	*pendingEnd = nullptr;
+	if (!c->profiling) return;
+	cudaEvent_t start = nextEvent(c);
+	*pendingEnd = nextEvent(c);
+	c->eventKind.push_back(kind);
+	cudaEventRecord(start, c->stream);
+}
+void spanEnd(ipic_ctx* c, cudaEvent_t* pendingEnd) {
+	if (*pendingEnd) cudaEventRecord(*pendingEnd, c->stream);
+	*pendingEnd = nullptr;
+}
+
 // the whole universe on one GPU: no exchange
 int enqueueStepSingle(ipic_ctx* c, const StepFlags& f, int stepIndex) {
 	if (f.project && f.interp) {
@@ -871,6 +890,7 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 		if (!f.fuseDeposit) fieldPhase(c, f);
 		if (f.fuseDeposit) { int rc = waitPeersDoneWithCellJ(c); if (rc) return rc; }
 		// everything queued on the main stream so far (previous imports, field phase) comes first
+		spanBegin(c, 0, &c->moverSpanEnd);
 		CK(cudaEventRecord(c->evMainReady, c->stream));
 		CK(cudaStreamWaitEvent(c->bStream, c->evMainReady, 0));
 		if (c->group && f.migrate) {
@@ -878,22 +898,15 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 			CK(cudaStreamWaitEvent(c->bStream, neighbour(c, -1)->evRecv, 0));
 			CK(cudaStreamWaitEvent(c->bStream, neighbour(c, +1)->evRecv, 0));
 		}
-		{
-			ProfSpan span(c, 0, c->bStream);
-			launch_move(moveArgs(c, f, 0, 1), c->bStream);
-			c->launches++;
-			if (lz > 1) { launch_move(moveArgs(c, f, lz - 1, 1), c->bStream); c->launches++; }
-		}
+		launch_move(moveArgs(c, f, 0, 1), c->bStream);
+		c->launches++;
+		if (lz > 1) { launch_move(moveArgs(c, f, lz - 1, 1), c->bStream); c->launches++; }
 		if (f.migrate) { int rc = packFaces(c, stepIndex); if (rc) return rc; }
 		CK(cudaEventRecord(c->evPacked, c->bStream));
 		break;
 	}
 	case PH_INTERIOR:
-		if (lz > 2) {
-			ProfSpan span(c, 0);
-			launch_move(moveArgs(c, f, 1, lz - 2), c->stream);
-			c->launches++;
-		}
+		if (lz > 2) { launch_move(moveArgs(c, f, 1, lz - 2), c->stream); c->launches++; }
 		if (f.fuseDeposit) CK(cudaEventRecord(c->evMoved, c->stream));
 		break;
 	case PH_EXCHANGE: {
@@ -930,12 +943,16 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 		break;
 	case PH_IMPORT:
 		CK(cudaStreamWaitEvent(c->stream, c->evPacked, 0));   // the boundary planes' movers
+		spanEnd(c, &c->moverSpanEnd);
 		if (f.migrate) {
 			{
 				ProfSpan span(c, 1);
 				importPlanes(c, stepIndex, 1, lz - 2, false);
 			}
-			CK(cudaStreamWaitEvent(c->stream, c->evRecv, 0));
+			{
+				ProfSpan wait(c, 2);
+				CK(cudaStreamWaitEvent(c->stream, c->evRecv, 0));
+			}
 			ProfSpan span(c, 1);
 			importPlanes(c, stepIndex, 0, 1, lz == 1);
 			if (lz > 1) importPlanes(c, stepIndex, lz - 1, 1, true);
@@ -947,8 +964,12 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 		break;
 	case PH_FIELDS:
 		if (!f.fuseDeposit) break;
-		{ int rc = finishCurrent(c); if (rc) return rc; }
-		fieldPhase(c, f);
+		{
+			ProfSpan wait(c, 3);
+			int rc = finishCurrent(c);
+			if (rc) return rc;
+			fieldPhase(c, f);
+		}
 		break;
 	default: break;
 	}
@@ -1275,7 +1296,8 @@ int ipic_selftest(int device, uint64_t n, uint64_t seed, uint64_t* mismatches) {
 
 int ipic_profile_reset(ipic_ctx* c) {
 	if (!c) return fail(IPIC_ERR_ARG, "null context");
-	c->profiling = true; c->moverMs = 0; c->importMs = 0; c->launches = 0; c->eventsUsed = 0;
+	c->profiling = true; c->moverMs = 0; c->importMs = 0; c->launches = 0; c->eventsUsed = 0; c->eventKind.clear();
+	for (double& v : c->phaseMs) v = 0;
 	return IPIC_OK;
 }
 
@@ -1294,6 +1316,16 @@ int ipic_profile_get(ipic_ctx* c, double* moverMs, double* importMs, uint64_t* l
 int ipic_relayout_count(ipic_ctx* c, uint64_t* count) {
 	if (!c || !count) return fail(IPIC_ERR_ARG, "null argument");
 	*count = c->relayouts;
+	return IPIC_OK;
+}
+
+int ipic_profile_phases(ipic_ctx* c, double* ms4) {
+	if (!c || !ms4) return fail(IPIC_ERR_ARG, "null argument");
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	int rc = drainProfile(c);
+	if (rc) return rc;
+	for (int i = 0; i < 4; i++) ms4[i] = c->phaseMs[i];
 	return IPIC_OK;
 }
 

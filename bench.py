@@ -220,6 +220,7 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop()
     mover_ms, import_ms, launches = ctx.profile_get()
+    phases = [p / args.steps for p in ctx.profile_phases()]
     seconds = max_over_ranks(t_first + t_rest)
     pushes = args.steps * n_total                            # nothing is absorbed in the :U: universe (planetRadius = 0)
     value = pushes / seconds
@@ -232,6 +233,7 @@ def run_b200(args):
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "bytes_per_push": BYTES_PER_PUSH, "pushes_per_launch": n_local, "launch_ms": mover_s * 1e3,
                 "import_ms": import_ms / args.steps,
+                "phase_ms_rank0": {"movers": phases[0], "imports": phases[1], "wait_exchange": phases[2], "wait_current_and_fields": phases[3]},
                 "whole_step_frac": value / world * BYTES_PER_PUSH / 1e9 / hbm_peak}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):

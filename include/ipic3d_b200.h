@@ -152,6 +152,9 @@ IPIC_API int  ipic_selftest(int device, uint64_t n, uint64_t seed, uint64_t* mis
  * reset, and the number of kernel launches issued. */
 IPIC_API int  ipic_profile_reset(ipic_ctx* ctx);
 IPIC_API int  ipic_profile_get(ipic_ctx* ctx, double* mover_ms, double* import_ms, uint64_t* launches);
+/* Slab steps, accumulated ms on the main stream: [0] all movers (span from the first launch to the last one's end),
+ * [1] import kernels, [2] waiting for the face exchange, [3] waiting for the all-gathered current + J + field phase. */
+IPIC_API int  ipic_profile_phases(ipic_ctx* ctx, double* ms4);
 
 #ifdef __cplusplus
 }
