@@ -402,3 +402,34 @@ def uniform_universe(props, num_particles, z_begin=0, z_count=None, threads=0):
     if len(aos):
         uniform_particles_into(props, num_particles, aos.ctypes.data, z_begin, z_count, threads)
     return counts, aos
+
+
+def dipole_universe(deck_path, grid, per_dim):
+    """The reference's `ipic3d <deck>` universe (main()'s Earth set-up, two-phase initCells) built by the host C++ mirror,
+    with the deck's grid replaced by grid^3 cells (box length scaled to keep the cell width) and per_dim^3 particles per cell."""
+    import re
+    import tempfile
+    text = open(deck_path).read()
+    old = int(re.search(r"^nxc = (\d+)", text, re.M).group(1))
+    length = float(re.search(r"^Lx = ([0-9.]+)", text, re.M).group(1)) * grid / old
+    for k in ("nxc", "nyc", "nzc"):
+        text = re.sub(r"^%s = .*$" % k, "%s = %d" % (k, grid), text, flags=re.M)
+    for k in ("Lx", "Ly", "Lz"):
+        text = re.sub(r"^%s = .*$" % k, "%s = %r" % (k, length), text, flags=re.M)
+    for k in ("npcelx", "npcely", "npcelz"):
+        text = re.sub(r"^%s = .*$" % k, "%s = %d %d" % (k, per_dim, per_dim), text, flags=re.M)
+    lib = load_host_library()
+    lib.ipic_mirror_create_from_inp.restype = C.c_void_p
+    lib.ipic_mirror_total.restype = C.c_uint64
+    with tempfile.NamedTemporaryFile("w", suffix=".inp", delete=False) as f:
+        f.write(text)
+    props = Props()
+    h = C.c_void_p(lib.ipic_mirror_create_from_inp(f.name.encode(), C.byref(props), None, None))
+    os.unlink(f.name)
+    n = lib.ipic_mirror_total(h)
+    counts = np.zeros(props.ncells, dtype=np.uint64)
+    aos = np.empty((n, 8), dtype=np.float64)
+    lib.ipic_mirror_get_counts(h, _up(counts))
+    lib.ipic_mirror_get_particles(h, _dp(aos))
+    lib.ipic_mirror_destroy(h)
+    return props, counts, aos

@@ -37,6 +37,10 @@ def parse_args():
     ap.add_argument("--particles-per-gpu", type=int, default=32_000_000)
     ap.add_argument("--grid", type=int, default=32)
     ap.add_argument("--no-deposit", action="store_true", help="time the loop as the reference ships it (STEP 1 off)")
+    ap.add_argument("--workload", default="uniform", choices=["uniform", "dipole"],
+                    help="uniform = the headline :U:N plasma; dipole = a secondary, single-GPU data point: the reference's Earth-dipole "
+                         ".inp set-up (medium.inp physics: 0.625 R_E cells, 10 MeV protons, absorption, ~17 %% migration per step) on --grid^3 "
+                         "cells with 8^3 particles per cell")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-particles", type=int, default=8_000_000, help="size of the bounded CPU sample")
@@ -188,17 +192,25 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    props = capi.uniform_benchmark_props(args.grid)
     nz = args.grid
     if nz % world:
         raise SystemExit("grid z extent %d not divisible by %d ranks" % (nz, world))
     lz = nz // world
-    n_total = args.particles_per_gpu * world
-    counts = capi.uniform_counts(props, n_total, rank * lz, lz)
-    n_local = int(counts.sum())
-    # the host universe of this slab, pinned (what simulateSteps hands to the C ABI)
-    host = torch.empty((n_local, 8), dtype=torch.float64).pin_memory()
-    capi.uniform_particles_into(props, n_total, host.data_ptr(), rank * lz, lz)
+    if args.workload == "dipole":
+        if world != 1:
+            raise SystemExit("--workload dipole is a single-GPU data point")
+        props, counts, aos = capi.dipole_universe(os.path.join(ROOT, "tests", "golden", "inputs", "medium.inp"), args.grid, 8)
+        n_total = n_local = int(counts.sum())
+        host = torch.from_numpy(aos).pin_memory()
+        del aos
+    else:
+        props = capi.uniform_benchmark_props(args.grid)
+        n_total = args.particles_per_gpu * world
+        counts = capi.uniform_counts(props, n_total, rank * lz, lz)
+        n_local = int(counts.sum())
+        # the host universe of this slab, pinned (what simulateSteps hands to the C ABI)
+        host = torch.empty((n_local, 8), dtype=torch.float64).pin_memory()
+        capi.uniform_particles_into(props, n_total, host.data_ptr(), rank * lz, lz)
     result = torch.empty((n_local + n_local // 8 + 4096, 8), dtype=torch.float64).pin_memory()
 
     flags = 0 if args.no_deposit else ipic.PROJECT_CURRENT
@@ -222,9 +234,11 @@ def run_b200(args):
     mover_ms, import_ms, launches = ctx.profile_get()
     phases = [p / args.steps for p in ctx.profile_phases()]
     seconds = max_over_ranks(t_first + t_rest)
-    pushes = args.steps * n_total                            # nothing is absorbed in the :U: universe (planetRadius = 0)
-    value = pushes / seconds
     alive = ctx.total_particles()
+    # :U: universe: nothing is absorbed (planetRadius = 0).  Dipole: the planet absorbs particles; the metric follows the
+    # reference and counts the INITIAL population per step (benchmark.h:50 / ipic3d.cxx:96-99)
+    pushes = args.steps * n_total
+    value = pushes / seconds
 
     hbm_peak, peak_src = measured_peaks()
     mover_s = max_over_ranks(mover_ms / 1e3) / args.steps
@@ -286,10 +300,12 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": seconds / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "uniform plasma :U:N (reference generator, bit-identical), %dx%dx%d cells, %d particles per GPU, z-slabs"
-                                   % (args.grid, args.grid, args.grid, args.particles_per_gpu),
-                       "particles": n_total, "particles_per_gpu": args.particles_per_gpu, "grid": [args.grid] * 3,
-                       "dt": 0.15, "deposit": not args.no_deposit, "parallelism": "zslab%d" % world,
+            "config": {"workload": ("uniform plasma :U:N (reference generator, bit-identical), %dx%dx%d cells, %d particles per GPU, z-slabs"
+                                    % (args.grid, args.grid, args.grid, args.particles_per_gpu)) if args.workload == "uniform" else
+                                   ("SECONDARY: Earth-dipole .inp set-up of the reference (medium.inp physics, host mirror generator), %dx%dx%d cells, "
+                                    "8^3 particles per cell" % (args.grid, args.grid, args.grid)),
+                       "particles": n_total, "particles_per_gpu": n_total // world, "grid": [args.grid] * 3,
+                       "dt": float(props.dt), "deposit": not args.no_deposit, "parallelism": "zslab%d" % world,
                        "particle_fields_in_hbm": particle_fields,
                        "l2": "inputs (%.2f GB of particle state per GPU) are larger than L2; no flush needed" % (n_local * 64 / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

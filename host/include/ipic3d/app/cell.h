@@ -248,8 +248,8 @@ namespace ipic3d {
 
 		std::cout << "Populating cells ...\n";
 
-		// phase 2 (independent per cell)
-		forEachCoordinate(coordinate_type(0), grid, [&](const coordinate_type& pos) {
+		// phase 2 (independent per cell: own seed, own generators)
+		pfor(coordinate_type(0), grid, [&](const coordinate_type& pos) {
 			const detail::CellBox box = detail::cellBox(properties, pos);
 			Distribution mine = sampler;
 			mine.seed(box.seed);
@@ -278,7 +278,7 @@ namespace ipic3d {
 		const std::uint64_t numCells = (std::uint64_t)(grid.x * grid.y * grid.z);
 		const std::uint64_t perCell = numParticles / numCells, extra = numParticles % numCells;
 		std::cout << "  particles / cell: " << perCell << " (+1)\n";
-		forEachCoordinate(coordinate_type(0), grid, [&](const coordinate_type& pos) {
+		pfor(coordinate_type(0), grid, [&](const coordinate_type& pos) {
 			const detail::CellBox box = detail::cellBox(properties, pos);
 			distribution::uniform<> next(box.low, box.high, Vector3<double>{ -0.2, -0.2, -0.2 }, Vector3<double>{ +0.2, +0.2, +0.2 }, box.seed);
 			const std::uint64_t n = perCell + (cells.flatten(pos) < extra ? 1 : 0);

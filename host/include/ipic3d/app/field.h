@@ -51,7 +51,7 @@ namespace ipic3d {
 	inline Field initFields(const InitProperties& initProperties, const UniverseProperties& universeProperties) {
 		const coordinate_type one(1);
 		Field fields(universeProperties.size + coordinate_type(3));
-		forEachCoordinate(one, universeProperties.size + coordinate_type(2), [&](const coordinate_type& cur) {
+		pfor(one, universeProperties.size + coordinate_type(2), [&](const coordinate_type& cur) {
 			fields[cur] = getDipoleFieldAt(getLocationForFields(cur - one, universeProperties), initProperties, universeProperties);
 		});
 		return fields;

@@ -6,9 +6,13 @@
 // surface is provided here as plain host containers: element-wise arithmetic, dominance tests,
 // "[a,b,c]" printing, a dense value-initialised 3-D grid flattened (x*Ny + y)*Nz + z.
 #pragma once
+#include <algorithm>
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <ostream>
+#include <thread>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -102,12 +106,39 @@ namespace ipic3d {
 		template<typename Body> void forEach(const Body& body) { for (auto& c : cells) body(c); }
 	};
 
-	// sequential stand-in for the `pfor(begin, end, body)` loops of the host-side set-up code
+	// sequential counterpart of the reference's `pfor(begin, end, body)` / `forEach` loops, lexicographic order
 	template<typename Body>
 	void forEachCoordinate(const coordinate_type& begin, const coordinate_type& end, const Body& body) {
 		for (std::int64_t i = begin.x; i < end.x; ++i)
 			for (std::int64_t j = begin.y; j < end.y; ++j)
 				for (std::int64_t k = begin.z; k < end.z; ++k) body(coordinate_type{ i, j, k });
+	}
+
+	// `pfor` proper: the body is called once per coordinate from a pool of host threads, in no particular order.
+	// Only for bodies that touch nothing but their own coordinate's data (per-cell initialisation: every cell has
+	// its own seed, so the result does not depend on the schedule).  NUM_WORKERS caps the threads like in the
+	// reference's runs.
+	template<typename Body>
+	void pfor(const coordinate_type& begin, const coordinate_type& end, const Body& body) {
+		const std::int64_t ny = end.y - begin.y, nz = end.z - begin.z;
+		const std::int64_t total = (end.x - begin.x) * ny * nz;
+		if (total <= 0) return;
+		unsigned workers = std::thread::hardware_concurrency();
+		if (const char* e = std::getenv("NUM_WORKERS")) workers = (unsigned)std::atoi(e);
+		workers = std::max(1u, std::min(workers, 64u));
+		if (total < 64 || workers == 1) { forEachCoordinate(begin, end, body); return; }
+		std::atomic<std::int64_t> next(0);
+		auto work = [&]() {
+			for (;;) {
+				const std::int64_t t = next.fetch_add(1);
+				if (t >= total) return;
+				body(coordinate_type{ begin.x + t / (ny * nz), begin.y + (t / nz) % ny, begin.z + t % nz });
+			}
+		};
+		std::vector<std::thread> pool;
+		for (unsigned w = 1; w < workers; ++w) pool.emplace_back(work);
+		work();
+		for (auto& t : pool) t.join();
 	}
 
 } // namespace ipic3d
