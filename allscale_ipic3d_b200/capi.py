@@ -22,6 +22,7 @@ API_SYMBOLS = [
     "ipic_step_async", "ipic_sync", "ipic_count_misplaced", "ipic_profile_reset", "ipic_profile_get", "ipic_selftest",
     "ipic_set_exchange_capacity", "ipic_group_create", "ipic_group_step", "ipic_relayout_count",
     "ipic_alloc_pinned", "ipic_free_pinned", "ipic_set_uniform_species", "ipic_particle_fields", "ipic_profile_phases",
+    "ipic_diagnostics", "ipic_group_diagnostics",
 ]
 
 
@@ -230,6 +231,12 @@ class Context:
         self._ck(self.lib.ipic_count_misplaced(self.h, C.byref(t)))
         return int(t.value)
 
+    def diagnostics(self):
+        """(total momentum, E energy, B energy, total kinetic energy): the columns of ConservedQuantities.out, reduced on the device."""
+        out = (C.c_double * 4)()
+        self._ck(self.lib.ipic_diagnostics(self.h, out))
+        return tuple(out)
+
     def profile_reset(self):
         self._ck(self.lib.ipic_profile_reset(self.h))
 
@@ -340,6 +347,13 @@ class Group:
 
     def count_misplaced(self):
         return sum(m.count_misplaced() for m in self.members)
+
+    def diagnostics(self):
+        out = (C.c_double * 4)()
+        rc = self.lib.ipic_group_diagnostics(self._handles, C.c_int(len(self.members)), out)
+        if rc:
+            raise IpicError(rc, self.lib.ipic_last_error().decode())
+        return tuple(out)
 
     def relayout_count(self):
         return sum(m.relayout_count() for m in self.members)

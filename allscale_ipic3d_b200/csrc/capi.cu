@@ -16,6 +16,7 @@
 
 #include "../../include/ipic3d_b200.h"
 #include "comm.h"
+#include "diag_kernels.h"
 #include "field_kernels.h"
 #include "ipic_device.cuh"
 #include "particle_kernels.h"
@@ -1274,6 +1275,40 @@ int ipic_count_misplaced(ipic_ctx* c, uint64_t* misplaced) {
 	CK(cudaStreamSynchronize(c->stream));
 	cudaFree(d);
 	*misplaced = h;
+	return IPIC_OK;
+}
+
+int ipic_diagnostics(ipic_ctx* c, double* out4) {
+	if (!c || !out4) return fail(IPIC_ERR_ARG, "null argument");
+	CK(cudaSetDevice(c->device));
+	const int64_t pairs = (int64_t)std::max(1, c->g.ncellsLocal) + kFieldEnergyChunks + 2;
+	int rc = ensureStage(c, 2 * pairs);
+	if (rc) return rc;
+	double* cellPart = c->dStage;
+	double* fieldPart = cellPart + 2 * (int64_t)std::max(1, c->g.ncellsLocal);
+	double* res = fieldPart + 2 * kFieldEnergyChunks;                  // { KE, momentum, E energy, B energy }
+	if (c->haveCells) launch_particle_energy(c->g, c->buf[c->cur], c->dCellStart, c->dCount, cellPart, res, c->stream);
+	else CK(cudaMemsetAsync(res, 0, 2 * sizeof(double), c->stream));
+	launch_field_energy(c->g, c->dEB, c->dBext, fieldPart, kFieldEnergyChunks, res + 2, c->stream);
+	c->launches += c->haveCells ? 4 : 2;
+	double h[4];
+	CK(cudaMemcpyAsync(h, res, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	out4[0] = h[1]; out4[1] = h[2]; out4[2] = h[3]; out4[3] = h[0];
+	return IPIC_OK;
+}
+
+int ipic_group_diagnostics(ipic_ctx** ctxs, int n, double* out4) {
+	if (!ctxs || n < 1 || !out4) return fail(IPIC_ERR_ARG, "bad group arguments");
+	double mom = 0.0, ke = 0.0;
+	for (int r = 0; r < n; r++) {
+		double d[4];
+		int rc = ipic_diagnostics(ctxs[r], d);
+		if (rc) return rc;
+		mom += d[0]; ke += d[3];
+		if (r == 0) { out4[1] = d[1]; out4[2] = d[2]; }
+	}
+	out4[0] = mom; out4[3] = ke;
 	return IPIC_OK;
 }
 

@@ -326,6 +326,29 @@ namespace ipic3d {
 		return cells;
 	}
 
+	// ---- conserved-quantity folds over a host universe (reference hdr/cell.h:1315-1355) --------------------------
+	// Sequential, in the reference's order (particles in cell order; cells lexicographic).  simulateSteps does not use
+	// them: while the universe is on the GPU the same sums come from ipic_diagnostics (device tree reductions).
+
+	inline double getParticlesKineticEnergy(const Cell& cell) {
+		double res = 0.0;
+		for (const Particle& p : cell.particles) res += 0.5 * (p.q / p.qom) * sumOfSquares(p.velocity);
+		return res;
+	}
+
+	inline double getParticlesMomentum(const Cell& cell) {
+		double res = 0.0;
+		for (const Particle& p : cell.particles) res += (p.q / p.qom) * std::sqrt(sumOfSquares(p.velocity));
+		return res;
+	}
+
+	template<class T>
+	double getTotalParticlesEnergy(const Cells& cells, T func) {
+		double res = 0.0;
+		forEachCoordinate(coordinate_type(0), cells.size(), [&](const coordinate_type& index) { res += func(cells[index]); });
+		return res;
+	}
+
 	// ---- outputs (reference hdr/cell.h:1360-1429) ---------------------------------------------------------------
 
 	// "<base>.out": "[Nx,Ny,Nz]", one "x,y,z:count" line per cell in x-major order, a blank line, "Total: n"

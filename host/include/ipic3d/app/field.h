@@ -4,6 +4,8 @@
 // (csrc/field_kernels.cu).
 #pragma once
 #include <cmath>
+#include <fstream>
+#include <string>
 
 #include "ipic3d/app/init_properties.h"
 #include "ipic3d/app/universe_properties.h"
@@ -69,6 +71,41 @@ namespace ipic3d {
 		BcField bcfield(universeProperties.size + coordinate_type(2));
 		forEachCoordinate(coordinate_type(1), universeProperties.size + coordinate_type(1), [&](const coordinate_type& cur) { interpN2C(cur, field, bcfield); });
 		return bcfield;
+	}
+
+	// field energy over the nodes [1, size-1) of the field grid: sum of 0.5 * cell volume * |F|^2 / (4 pi), F chosen by the
+	// accessor (reference hdr/field.h:443-459); sequential fold in lexicographic order
+	template<typename Accessor>
+	double getFieldEnergy(const Field& field, const UniverseProperties& universeProperties, const Accessor& accessor) {
+		const double vol = 0.5 * universeProperties.cellWidth.x * universeProperties.cellWidth.y * universeProperties.cellWidth.z;
+		const double fourPI = 16.0 * std::atan(1.0);
+		double res = 0.0;
+		forEachCoordinate(coordinate_type(1), field.size() - coordinate_type(1), [&](const coordinate_type& index) {
+			res += vol * sumOfSquares(accessor(field, index)) / (fourPI);
+		});
+		return res;
+	}
+
+	// dump of all field values: "[Nx,Ny,Nz]", then "i,j,k:E|B|Bext" per node, blank line; the same for Bc
+	// (reference hdr/field.h:464-530: two consecutive dumps into the entry of that name; never called by the reference's
+	// drivers or tests)
+	inline void outputFieldGrids(const Field& field, const BcField& bcField, const std::string& outputFilename) {
+		{
+			std::ofstream out(outputFilename);
+			out << field.size() << "\n";
+			forEachCoordinate(coordinate_type(0), field.size(), [&](const coordinate_type& p) {
+				out << p.x << "," << p.y << "," << p.z << ":" << field[p].E << "|" << field[p].B << "|" << field[p].Bext << "\n";
+			});
+			out << "\n";
+		}
+		{
+			std::ofstream out(outputFilename, std::ios::app);
+			out << bcField.size() << "\n";
+			forEachCoordinate(coordinate_type(0), bcField.size(), [&](const coordinate_type& p) {
+				out << p.x << "," << p.y << "," << p.z << ":" << bcField[p].Bc << "\n";
+			});
+			out << "\n";
+		}
 	}
 
 	inline CurrentDensity initCurrentDensity(const UniverseProperties& universeProperties) {

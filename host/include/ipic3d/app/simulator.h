@@ -21,6 +21,8 @@
 // IPIC3D_DEVICES=<ordinal,ordinal,...> names the slabs' devices explicitly.
 #pragma once
 #include <chrono>
+#include <cstdio>
+#include <fstream>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -136,6 +138,63 @@ namespace ipic3d {
 		};
 	}
 
+	// ---- conserved-quantity log and density snapshots (reference hdr/simulator.h:64-115, ENABLE_DEBUG_OUTPUT) --------
+
+	template<typename StreamObject>
+	void writeOutputHeader(StreamObject& streamObject) {
+		streamObject << "Cycle \t Total Moment \t E energy \t B energy \t Total KE \n";
+	}
+
+	namespace detail {
+		// is the cycle one that writeOutputData logs (simulator.h:74) / dumps the density of (simulator.h:93)?
+		inline bool fieldOutputDue(const UniverseProperties& p, std::uint64_t cycle, std::uint64_t numSteps) {
+			return p.FieldOutputCycle > 0 && ((cycle % (std::uint64_t)p.FieldOutputCycle == 0) || (cycle + 1 == numSteps));
+		}
+		inline bool particleOutputDue(const UniverseProperties& p, std::uint64_t cycle) {
+			return p.ParticleOutputCycle > 0 && ((cycle == 0) || ((cycle + 1) % (std::uint64_t)p.ParticleOutputCycle == 0));
+		}
+		template<typename StreamObject>
+		void writeConservedRow(std::uint64_t cycle, const double q[4], StreamObject& streamObject) {
+			streamObject << cycle << "\t" << q[0] << "\t" << q[1] << "\t" << q[2] << "\t" << q[3] << "\n";
+		}
+		// "t,x,y,z,density" snapshot: number of particles per cell, cells in x-major order (simulator.h:93-113)
+		template<typename CountOf>
+		void writeDensitySnapshot(const UniverseProperties& p, std::uint64_t cycle, const char* fileName, const CountOf& countOf) {
+			const int t = (int)((cycle + 1) / (std::uint64_t)p.ParticleOutputCycle);
+			std::cout << cycle << ' ' << t << '\n';
+			char fileNamet[96];
+			std::snprintf(fileNamet, sizeof fileNamet, "%s%06d", fileName, t);
+			std::ofstream out(fileNamet);
+			out << "t,x,y,z,density\n";
+			for (std::int64_t x = 0; x < p.size.x; x++) for (std::int64_t y = 0; y < p.size.y; y++) for (std::int64_t z = 0; z < p.size.z; z++)
+				out << t << "," << x * p.cellWidth.x << "," << y * p.cellWidth.y << "," << z * p.cellWidth.z << "," << countOf(x, y, z) << "\n";
+		}
+		// the reference compiles the log in with -DENABLE_DEBUG_OUTPUT; here it can also be switched on at run time
+		inline bool debugOutputEnabled() {
+#ifdef ENABLE_DEBUG_OUTPUT
+			return true;
+#else
+			const char* e = std::getenv("IPIC3D_DEBUG_OUTPUT");
+			return e && std::atoi(e) != 0;
+#endif
+		}
+	}
+
+	// write output depending on the set frequency, from a universe that lives on the host (reference simulator.h:71-115)
+	template<typename StreamObject>
+	void writeOutputData(const int cycle, const int numSteps, Universe& universe, StreamObject& streamObject, char* fileName) {
+		const UniverseProperties& p = universe.properties;
+		if (detail::fieldOutputDue(p, (std::uint64_t)cycle, (std::uint64_t)numSteps)) {
+			auto getE = [](const Field& field, const coordinate_type& index) { return field[index].E; };
+			auto getB = [](const Field& field, const coordinate_type& index) { return field[index].B + field[index].Bext; };
+			const double q[4] = { getTotalParticlesEnergy(universe.cells, getParticlesMomentum), getFieldEnergy(universe.field, p, getE),
+			                      getFieldEnergy(universe.field, p, getB), getTotalParticlesEnergy(universe.cells, getParticlesKineticEnergy) };
+			detail::writeConservedRow((std::uint64_t)cycle, q, streamObject);
+		}
+		if (detail::particleOutputDue(p, (std::uint64_t)cycle))
+			detail::writeDensitySnapshot(p, (std::uint64_t)cycle, fileName, [&](std::int64_t x, std::int64_t y, std::int64_t z) { return universe.cells[{ x, y, z }].particles.size(); });
+	}
+
 	// frees the GPU contexts and pinned memory kept between simulateSteps calls
 	inline void releaseDevices() { detail::Session::instance().release(); }
 
@@ -159,6 +218,7 @@ namespace ipic3d {
 
 		const auto start = clock::now();
 		const UniverseProperties& props = universe.properties;
+		const bool debugOutput = detail::debugOutputEnabled();
 		const ipic_props abi = props.toAbi();
 		const std::int64_t nx = props.size.x, ny = props.size.y, nz = props.size.z;
 		const std::vector<int> devices = detail::slabDevices(nz);
@@ -199,17 +259,51 @@ namespace ipic3d {
 				if (!ps.empty()) std::memcpy(static_cast<char*>(staging.p) + offset[c] * sizeof(Particle), ps.data(), ps.size() * sizeof(Particle));
 			});
 			detail::check(ipic_upload_cells(ctx[(std::size_t)r], counts[(std::size_t)r].data(), static_cast<const double*>(staging.p)), "ipic_upload_cells");
-			if (usesFields || writesCurrent)
+			if (usesFields || writesCurrent || debugOutput)
 				detail::check(ipic_upload_fields(ctx[(std::size_t)r], reinterpret_cast<const double*>(universe.field.data()),
 				                                 reinterpret_cast<const double*>(universe.bcfield.data()),
 				                                 reinterpret_cast<const double*>(universe.currentDensity.data())), "ipic_upload_fields");
 		}
 
-		// ---- the time loop: first step and the rest are timed apart, as the reference does
-		double tFirst = 0, tRest = 0;
-		if (numSteps > 0) detail::check(ipic_group_step(ctx.data(), gpus, 1, flags, &tFirst, nullptr), "ipic_group_step");
-		const auto endFirst = clock::now();
-		if (numSteps > 1) detail::check(ipic_group_step(ctx.data(), gpus, numSteps - 1, flags, &tFirst, &tRest), "ipic_group_step");
+		// ---- the time loop: first step and the rest are timed apart, as the reference does.  With the debug output on
+		// (reference: -DENABLE_DEBUG_OUTPUT, simulator.h:160-187) the loop stops before every cycle that is logged; the
+		// four conserved quantities are reduced on the device (ipic_group_diagnostics) and the density snapshot needs the
+		// per-cell counts only, so the particles stay in HBM.
+		std::ofstream logFile;
+		char fileName[64] = "";
+		if (debugOutput) {
+			logFile.open(props.outputFileBaseName + "ConservedQuantities.out");
+			writeOutputHeader(logFile);
+			const auto timeStamp = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+			std::snprintf(fileName, sizeof fileName, "result_%ld.csv.", (long)timeStamp);
+		}
+		const auto emitOutput = [&](std::uint64_t cycle) {
+			if (detail::fieldOutputDue(props, cycle, numSteps)) {
+				double q[4];
+				detail::check(ipic_group_diagnostics(ctx.data(), gpus, q), "ipic_group_diagnostics");
+				detail::writeConservedRow(cycle, q, logFile);
+			}
+			if (detail::particleOutputDue(props, cycle)) {
+				std::vector<std::vector<std::uint64_t>> now((std::size_t)gpus);
+				for (int r = 0; r < gpus; ++r) {
+					now[(std::size_t)r].resize((std::size_t)(nx * ny * lz));
+					detail::check(ipic_cell_counts(ctx[(std::size_t)r], now[(std::size_t)r].data()), "ipic_cell_counts");
+				}
+				detail::writeDensitySnapshot(props, cycle, fileName, [&](std::int64_t x, std::int64_t y, std::int64_t z) {
+					return now[(std::size_t)(z / lz)][(std::size_t)((x * ny + y) * lz + z % lz)];
+				});
+			}
+		};
+		const auto outputDue = [&](std::uint64_t cycle) { return debugOutput && (detail::fieldOutputDue(props, cycle, numSteps) || detail::particleOutputDue(props, cycle)); };
+		auto endFirst = clock::now();
+		for (std::uint64_t done = 0; done < numSteps;) {
+			if (outputDue(done)) emitOutput(done);
+			std::uint64_t next = done + 1;                       // the first step is timed on its own
+			while (done > 0 && next < numSteps && !outputDue(next)) ++next;
+			detail::check(ipic_group_step(ctx.data(), gpus, next - done, flags, nullptr, nullptr), "ipic_group_step");
+			if (done == 0) endFirst = clock::now();
+			done = next;
+		}
 
 		// ---- download
 		for (int r = 0; r < gpus; ++r) {

@@ -192,6 +192,18 @@ IPIC_API void ipic_mirror_get_fields(void* handle, double* field, double* bc, do
 	std::memcpy(J, u.currentDensity.data(), u.currentDensity.count() * sizeof(ipic3d::DensityNode));
 }
 
+// host folds of the conserved quantities (cell.h / field.h mirror): { momentum, E energy, B energy, KE }
+IPIC_API void ipic_mirror_diagnostics(void* handle, double* out4) {
+	using namespace ipic3d;
+	const auto& u = static_cast<MirrorUniverse*>(handle)->universe;
+	auto getE = [](const Field& field, const coordinate_type& index) { return field[index].E; };
+	auto getB = [](const Field& field, const coordinate_type& index) { return field[index].B + field[index].Bext; };
+	out4[0] = getTotalParticlesEnergy(u.cells, getParticlesMomentum);
+	out4[1] = getFieldEnergy(u.field, u.properties, getE);
+	out4[2] = getFieldEnergy(u.field, u.properties, getB);
+	out4[3] = getTotalParticlesEnergy(u.cells, getParticlesKineticEnergy);
+}
+
 // the parser alone: values of every key the reference reads, as "name=value;" text (vectors comma separated)
 IPIC_API int ipic_mirror_parse(const char* path, char* out, int capacity) {
 	const ipic3d::Parameters p{ std::string(path) };

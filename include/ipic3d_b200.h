@@ -143,6 +143,16 @@ IPIC_API int  ipic_sync(ipic_ctx* ctx);
  * particles outside the closed box of their cell. */
 IPIC_API int  ipic_count_misplaced(ipic_ctx* ctx, uint64_t* misplaced);
 
+/* Conserved quantities of the state on the device, the four columns writeOutputData prints into
+ * <base>ConservedQuantities.out (simulator.h:71-91): out4 = { total particle momentum sum (q/qom)*|v|
+ * (getTotalParticlesEnergy(cells, getParticlesMomentum), cell.h:1330-1355), E field energy, B + Bext field
+ * energy (getFieldEnergy, field.h:443-459), total kinetic energy (getParticlesKineticEnergy, cell.h:1315-1325) }.
+ * Deterministic tree reductions on the device: no particle leaves the GPU.  For a slab context the two
+ * particle sums cover the slab's own cells (the field grids are replicated); ipic_group_diagnostics adds the
+ * members' sums in rank order. */
+IPIC_API int  ipic_diagnostics(ipic_ctx* ctx, double* out4);
+IPIC_API int  ipic_group_diagnostics(ipic_ctx** ctxs, int n, double* out4);
+
 /* Device self-test of the FP64 helpers that replace library code on the hot path (shared-reciprocal
  * division of the Boris rotation): number of random inputs (out of n) whose result is not bit-identical
  * to IEEE division.  Must be 0. */

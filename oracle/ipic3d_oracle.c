@@ -21,6 +21,8 @@
  *   orc_update_boundaries   <- updateFieldsOnBoundaries         hdr/field.h:407-440
  *   orc_init_fields         <- initFields/getDipoleFieldAt/initBcFields hdr/field.h:43-137
  *   orc_step                <- simulateSteps loop body          hdr/simulator.h:181-230
+ *   orc_diagnostics         <- writeOutputData columns          hdr/simulator.h:71-91 (getFieldEnergy hdr/field.h:443-459,
+ *                              getParticlesKineticEnergy / getParticlesMomentum / getTotalParticlesEnergy hdr/cell.h:1315-1355)
  *
  * Floating point: every expression keeps the reference's association order; compile with
  * -ffp-contract=off (no FMA), as x86-64 GCC does for the reference itself.
@@ -125,6 +127,37 @@ uint64_t orc_count_misplaced(const orc_universe* u) {
 		for (uint64_t i = 0; i < l->n; i++) if (!is_inside(&u->props, pos, l->p + i * 8)) bad++;
 	}
 	return bad;
+}
+
+/* ---- conserved quantities: simulator.h:71-91 ---------------------------------------------------
+ * out4 = { total momentum, E energy, B(+Bext) energy, total kinetic energy }; sequential folds in the
+ * reference's order: cells lexicographic, particles in cell order, per-cell sum first (cell.h:1315-1355);
+ * field nodes [1, size+2) lexicographic (field.h:443-459). */
+void orc_diagnostics(const orc_universe* u, double* out4) {
+	double mom = 0.0, ke = 0.0;
+	for (int64_t c = 0; c < u->ncells; c++) {
+		const plist* l = &u->cells[c];
+		double cm = 0.0, ck = 0.0;
+		for (uint64_t i = 0; i < l->n; i++) {
+			const double* p = l->p + i * 8;
+			double v2 = 0.0; v2 += p[3] * p[3]; v2 += p[4] * p[4]; v2 += p[5] * p[5];
+			ck += 0.5 * (p[6] / p[7]) * v2;
+			cm += (p[6] / p[7]) * sqrt(v2);
+		}
+		mom += cm; ke += ck;
+	}
+	const double vol = 0.5 * u->props.cellWidth[0] * u->props.cellWidth[1] * u->props.cellWidth[2];
+	const double fourPI = 16.0 * atan(1.0);
+	double eE = 0.0, eB = 0.0;
+	for (int64_t x = 1; x < u->nx + 2; x++) for (int64_t y = 1; y < u->ny + 2; y++) for (int64_t z = 1; z < u->nz + 2; z++) {
+		const double* f = u->field + fidx(u, x, y, z);
+		double e2 = 0.0; e2 += f[0] * f[0]; e2 += f[1] * f[1]; e2 += f[2] * f[2];
+		const double b0 = f[3] + f[6], b1 = f[4] + f[7], b2 = f[5] + f[8];
+		double bb = 0.0; bb += b0 * b0; bb += b1 * b1; bb += b2 * b2;
+		eE += vol * e2 / (fourPI);
+		eB += vol * bb / (fourPI);
+	}
+	out4[0] = mom; out4[1] = eE; out4[2] = eB; out4[3] = ke;
 }
 
 /* ---- Boris pusher: particle.h:24-49 ---------------------------------------------------------- */

@@ -27,6 +27,8 @@ void orc_get_counts(const orc_universe* u, uint64_t* counts);
 void orc_get_particles(const orc_universe* u, double* aos);
 uint64_t orc_total_particles(const orc_universe* u);
 uint64_t orc_count_misplaced(const orc_universe* u);
+/* { total momentum, E energy, B+Bext energy, total kinetic energy }: the columns of ConservedQuantities.out */
+void orc_diagnostics(const orc_universe* u, double* out4);
 
 void orc_set_field(orc_universe* u, const double* field);     /* (n+3)^3 x 9 */
 void orc_get_field(const orc_universe* u, double* field);

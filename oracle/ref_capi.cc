@@ -278,6 +278,17 @@ void ref_write_counts(void* h, const char* filename) {
 	outputNumberOfParticlesPerCell(static_cast<Handle*>(h)->universe.cells, std::string(filename));
 }
 
+// the four columns writeOutputData prints (simulator.h:71-91), computed by the reference's own reductions
+void ref_diagnostics(void* h, double* out4) {
+	Universe& universe = static_cast<Handle*>(h)->universe;
+	auto getE = [](const auto& field, const auto& index) { return field[index].E; };
+	auto getB = [](const auto& field, const auto& index) { return (field[index].B + field[index].Bext); };
+	out4[0] = getTotalParticlesEnergy(universe.cells, getParticlesMomentum);
+	out4[1] = getFieldEnergy(universe.field, universe.properties, getE);
+	out4[2] = getFieldEnergy(universe.field, universe.properties, getB);
+	out4[3] = getTotalParticlesEnergy(universe.cells, getParticlesKineticEnergy);
+}
+
 uint64_t ref_count_misplaced(void* h) {
 	auto& u = static_cast<Handle*>(h)->universe;
 	auto s = u.cells.size();

@@ -129,6 +129,12 @@ class _Universe:
         f.restype = C.c_uint64
         return int(f(self.h))
 
+    def diagnostics(self):
+        """(total momentum, E energy, B energy, total kinetic energy) -- the columns of ConservedQuantities.out"""
+        out = np.zeros(4)
+        self._f("diagnostics")(self.h, _dp(out))
+        return out
+
     # -- fields --
     def _grid(self, name, extra, width, value=None):
         n = self.props.grid_len(extra)

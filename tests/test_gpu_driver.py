@@ -51,3 +51,37 @@ def test_uniform_benchmark_runs(tmp_path):
     assert "particles / cell: 61 (+1)" in text
     m = re.search(r"Throughput: ([0-9.e+]+) particles/s", text)
     assert m and float(m.group(1)) > 1e7
+
+
+REF_DBG = os.path.join(ROOT, "oracle", "_ref", "ipic3d_ref_dbg")
+
+
+@pytest.mark.parametrize("devices", [None, "0,0"])
+def test_conserved_quantities_log_and_density_snapshots(tmp_path, devices):
+    """The reference's ENABLE_DEBUG_OUTPUT products (simulator.h:64-115, :160-187) for test.inp (FieldOutputCycle 1,
+    ParticlesOutputCycle 10): `testConservedQuantities.out` (cycle, total momentum, E energy, B energy, total KE; the
+    sums come from ipic_group_diagnostics on the device) agrees with the reference's file to its 6 printed digits, and
+    the `result_<stamp>.csv.NNNNNN` per-cell density snapshots (counts only) are identical."""
+    if not os.path.exists(REF_DBG):
+        pytest.skip("oracle/_ref/ipic3d_ref_dbg not built")
+    a, b = tmp_path / "ours", tmp_path / "ref"
+    a.mkdir(); b.mkdir()
+    env = {"IPIC3D_DEBUG_OUTPUT": "1"}
+    if devices:
+        env["IPIC3D_DEVICES"] = devices
+    run(DRIVER, DECK, str(a), env)
+    run(REF_DBG, DECK, str(b))
+    ours = (a / "testConservedQuantities.out").read_text().splitlines()
+    want = (b / "testConservedQuantities.out").read_text().splitlines()
+    assert ours[0] == want[0] and len(ours) == len(want) == 31
+    for lo, lw in zip(ours[1:], want[1:]):
+        fo, fw = lo.split("\t"), lw.split("\t")
+        assert fo[0] == fw[0] and len(fo) == len(fw) == 5
+        for x, y in zip(fo[1:], fw[1:]):
+            assert abs(float(x) - float(y)) <= 2e-6 * abs(float(y)), (lo, lw)      # one unit in the 6th printed digit
+    snaps_o = sorted(p.name.split(".")[-1] for p in a.glob("result_*.csv.*"))
+    snaps_w = sorted(p.name.split(".")[-1] for p in b.glob("result_*.csv.*"))
+    assert snaps_o == snaps_w == ["000000", "000001", "000002", "000003"]
+    for s in snaps_o:
+        assert next(a.glob("result_*.csv." + s)).read_text() == next(b.glob("result_*.csv." + s)).read_text()
+    assert sorted((a / "test.out").read_text().split("\n")) == sorted((b / "test.out").read_text().split("\n"))

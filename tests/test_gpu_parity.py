@@ -473,3 +473,51 @@ def test_slabs_agree_on_layout():
             assert grp.particle_fields() == want_fields
             gc, ga = grp.download_cells()
         assert np.array_equal(gc, o.counts()) and bits_equal(ga, o.particles())
+
+
+def test_diagnostics_match_oracle(golden_dir):
+    """ipic_diagnostics (device tree reductions) vs the sequential folds of writeOutputData (simulator.h:71-91): total
+    momentum, E energy, B energy, total kinetic energy within 1e-12 relative, after 2 full PIC steps; a group of 2 slabs
+    gives the same numbers (partials added in rank order); an 8-field (two-species) universe too."""
+    g = np.load(os.path.join(golden_dir, "small_fields.npz"))
+    props = load_props(g["props"])
+    flags = harness.MOVER_INTERPOLATED | harness.PROJECT_CURRENT | harness.UPDATE_BOUNDARIES | harness.SOLVER_FORWARD
+    o = Oracle(props)
+    o.set_cells(g["counts0"], g["p0"])
+    o.field(g["field0"]); o.bcfield(g["bc0"])
+    nslabs = 2 if props.size[2] % 2 == 0 else int(props.size[2])
+    with ctx_for(props) as c, group_for(props, nslabs) as grp:
+        for u in (c, grp):
+            u.upload_cells(g["counts0"], g["p0"])
+            u.upload_fields(g["field0"], g["bc0"], None)
+        for step in range(3):
+            want = o.diagnostics()
+            for u in (c, grp):
+                got = np.array(u.diagnostics())
+                assert np.all(np.abs(got - want) <= TOL * np.abs(want)), (step, got, want)
+            assert all(v > 0 for v in want)
+            o.step(1, flags); c.step(1, flags); grp.step(1, flags)
+    # per-particle species (8-field layout): make every third particle a proton-like species
+    p = g["p0"].copy()
+    p[::3, 6] = 1.0; p[::3, 7] = 0.5
+    o.set_cells(g["counts0"], p)
+    with ctx_for(props) as c:
+        c.upload_cells(g["counts0"], p)
+        assert c.particle_fields() == 8
+        got, want = np.array(c.diagnostics()), o.diagnostics()
+        assert abs(got[0] - want[0]) <= TOL * abs(want[0]) and abs(got[3] - want[3]) <= TOL * abs(want[3])
+
+
+def test_diagnostics_uniform_benchmark():
+    """:U:1000000 after 3 steps: kinetic energy and momentum are conserved by the field-free mover bit for bit in every
+    particle, so the device reduction must reproduce the oracle's sequential sums to 1e-12."""
+    ref = Ref.uniform(1_000_000)
+    o = Oracle(ref.props)
+    o.set_cells(ref.counts(), ref.particles())
+    with ctx_for(ref.props) as c:
+        c.upload_cells(ref.counts(), ref.particles())
+        c.step(3); o.step(3)
+        got, want = np.array(c.diagnostics()), o.diagnostics()
+    assert want[1] == 0.0 and want[2] == 0.0 and got[1] == 0.0 and got[2] == 0.0
+    for i in (0, 3):
+        assert abs(got[i] - want[i]) <= TOL * abs(want[i])

@@ -78,6 +78,20 @@ def parse_with(fn, path):
     return buf.value.decode()
 
 
+def test_conserved_quantity_folds_bit_identical(mirror):
+    """getTotalParticlesEnergy / getParticlesMomentum / getParticlesKineticEnergy / getFieldEnergy of the host mirror
+    (cell.h:1315-1355, field.h:443-459) on the test.inp universe: bit-identical to the reference's."""
+    path = os.path.join(GOLDEN_INPUTS, "test.inp")
+    props, cycles, npart = Props(), C.c_uint64(0), C.c_uint64(0)
+    h = C.c_void_p(mirror.ipic_mirror_create_from_inp(path.encode(), C.byref(props), C.byref(cycles), C.byref(npart)))
+    got = np.zeros(4)
+    mirror.ipic_mirror_diagnostics(h, got.ctypes.data_as(C.POINTER(C.c_double)))
+    mirror.ipic_mirror_destroy(h)
+    ref = Ref.from_inp(path)
+    want = ref.diagnostics()
+    assert bits_equal(got, want) and got[0] > 0 and got[2] > 0 and got[3] > 0
+
+
 @pytest.mark.parametrize("deck", ["test.inp", "tiny.inp", "medium.inp"])
 def test_parser_matches_reference(mirror, deck):
     path = os.path.join(GOLDEN_INPUTS, deck)

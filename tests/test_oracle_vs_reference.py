@@ -90,6 +90,31 @@ def test_field_init_bit_exact():
     assert bits_equal(r.field(), o.field()) and bits_equal(r.bcfield(), o.bcfield())
 
 
+def test_diagnostics_match_reference(golden_dir):
+    """The four columns of ConservedQuantities.out (writeOutputData, simulator.h:71-91): oracle == reference bit for bit,
+    on a dipole universe with initialised fields (test.inp after 2 steps) and on the small full-PIC fixture."""
+    r = Ref.from_inp(os.path.join(golden_dir, "inputs", "test.inp"))
+    r.init_fields((0.0, 0.0, 0.0), (0.0, 0.0, 0.0))
+    r.step(2)
+    o = Oracle(r.props)
+    o.set_cells(r.counts(), r.particles())
+    o.field(r.field())
+    d = r.diagnostics()
+    assert bits_equal(d, o.diagnostics())
+    assert d[0] > 0 and d[3] > 0 and d[2] > 0 and d[1] == 0.0
+    g = np.load(os.path.join(golden_dir, "small_fields.npz"))
+    import ctypes
+    props = Props(); ctypes.memmove(ctypes.byref(props), g["props"].tobytes(), ctypes.sizeof(props))
+    r, o = Ref.empty(props), Oracle(props)
+    for u in (r, o):
+        u.set_cells(g["counts0"], g["p0"])
+        u.field(g["field0"]); u.bcfield(g["bc0"])
+    flags = harness.MOVER_INTERPOLATED | harness.PROJECT_CURRENT | harness.UPDATE_BOUNDARIES | harness.SOLVER_FORWARD
+    r.step(2, flags); o.step(2, flags)
+    assert bits_equal(r.diagnostics(), o.diagnostics())
+    assert all(v > 0 for v in r.diagnostics())
+
+
 def test_unit_functions_random():
     rng = np.random.default_rng(7)
     for _ in range(200):
