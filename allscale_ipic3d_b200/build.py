@@ -4,7 +4,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["capi.cu", "particle_kernels.cu", "field_kernels.cu", "diag_kernels.cu", "comm.cu"]
+SOURCES = ["capi.cu", "particle_kernels.cu", "field_kernels.cu", "diag_kernels.cu", "tracer_kernels.cu", "comm.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-fmad=false",            # no FMA contraction: bit-faithful FP64 vs the reference's x86-64 GCC build
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "-diag-suppress", "128"]
@@ -21,13 +21,14 @@ def needs_build(out):
 HOST_DIR = os.path.join(HERE, "..", "host")
 HOST_SRC = os.path.join(HOST_DIR, "src", "host_capi.cc")
 HOST_MAIN = os.path.join(HOST_DIR, "src", "ipic3d.cc")
+HOST_TRACER = os.path.join(HOST_DIR, "src", "pic_tracer.cc")
 HOST_INC = ["-I" + os.path.join(HOST_DIR, "include"), "-I" + os.path.join(HERE, "..", "include")]
 HOST_FLAGS = ["-O2", "-std=c++17", "-pthread", "-ffp-contract=off"]      # no FMA contraction: the init must be bit-faithful
 
 
 def _host_deps():
     inc = os.path.join(HOST_DIR, "include", "ipic3d", "app")
-    return [os.path.join(inc, f) for f in os.listdir(inc)] + [HOST_SRC, HOST_MAIN, os.path.join(HERE, "..", "include", "ipic3d_b200.h"), __file__]
+    return [os.path.join(inc, f) for f in os.listdir(inc)] + [HOST_SRC, HOST_MAIN, HOST_TRACER, os.path.join(HERE, "..", "include", "ipic3d_b200.h"), __file__]
 
 
 def build_host(force=False):
@@ -47,8 +48,10 @@ def build_driver(force=False):
     lib = os.path.join(HERE, "lib", "libipic3d_b200.so")
     if not force and os.path.exists(out) and all(os.path.getmtime(out) > os.path.getmtime(d) for d in _host_deps() + [lib]):
         return out
-    subprocess.check_call(["g++"] + HOST_FLAGS + HOST_INC + ["-o", out, HOST_MAIN, "-L" + os.path.join(HERE, "lib"), "-lipic3d_b200",
-                           "-Wl,-rpath,$ORIGIN/../../allscale_ipic3d_b200/lib"])
+    link = ["-L" + os.path.join(HERE, "lib"), "-lipic3d_b200", "-Wl,-rpath,$ORIGIN/../../allscale_ipic3d_b200/lib"]
+    subprocess.check_call(["g++"] + HOST_FLAGS + HOST_INC + ["-o", out, HOST_MAIN] + link)
+    # host/bin/pic_tracer_b200: the reference's `pic_tracer` (code/app/src/pic_tracer.cxx)
+    subprocess.check_call(["g++"] + HOST_FLAGS + HOST_INC + ["-o", os.path.join(HOST_DIR, "bin", "pic_tracer_b200"), HOST_TRACER] + link)
     return out
 
 

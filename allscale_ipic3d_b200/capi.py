@@ -22,7 +22,7 @@ API_SYMBOLS = [
     "ipic_step_async", "ipic_sync", "ipic_count_misplaced", "ipic_profile_reset", "ipic_profile_get", "ipic_selftest",
     "ipic_set_exchange_capacity", "ipic_group_create", "ipic_group_step", "ipic_relayout_count",
     "ipic_alloc_pinned", "ipic_free_pinned", "ipic_set_uniform_species", "ipic_particle_fields", "ipic_profile_phases",
-    "ipic_diagnostics", "ipic_group_diagnostics",
+    "ipic_diagnostics", "ipic_group_diagnostics", "ipic_trace",
 ]
 
 
@@ -357,6 +357,21 @@ class Group:
 
     def relayout_count(self):
         return sum(m.relayout_count() for m in self.members)
+
+
+def trace(props, aos, timesteps, frame_interval, device=0):
+    """pic_tracer's traceParticle over all particles of `aos` ((n, 8) float64): returns (counts[frames, nx, ny, nz] uint32, seconds)."""
+    lib = load_library()
+    aos = np.ascontiguousarray(aos, dtype=np.float64).reshape(-1, 8)
+    frames = (max(timesteps, 1) - 1) // max(frame_interval, 1) + 1
+    counts = np.zeros((frames, int(props.size[0]), int(props.size[1]), int(props.size[2])), dtype=np.uint32)
+    sec = C.c_double(0)
+    p = props if isinstance(props, Props) else Props.from_other(props)
+    rc = lib.ipic_trace(C.byref(p), C.c_int(device), aos.ctypes.data_as(C.POINTER(C.c_double)), C.c_uint64(len(aos)), C.c_int(timesteps),
+                        C.c_int(frame_interval), C.c_int(frames), counts.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(sec))
+    if rc:
+        raise IpicError(rc, lib.ipic_last_error().decode())
+    return counts, sec.value
 
 
 def selftest(n=1 << 22, seed=1, device=0):

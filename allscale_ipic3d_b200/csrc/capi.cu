@@ -20,6 +20,7 @@
 #include "field_kernels.h"
 #include "ipic_device.cuh"
 #include "particle_kernels.h"
+#include "tracer_kernels.h"
 
 using namespace ipic;
 
@@ -1309,6 +1310,57 @@ int ipic_group_diagnostics(ipic_ctx** ctxs, int n, double* out4) {
 		if (r == 0) { out4[1] = d[1]; out4[2] = d[2]; }
 	}
 	out4[0] = mom; out4[3] = ke;
+	return IPIC_OK;
+}
+
+int ipic_trace(const ipic_props* props, int device, const double* aos, uint64_t n, int timesteps, int frameInterval, int numFrames,
+               uint32_t* counts, double* seconds) {
+	if (seconds) *seconds = 0;
+	if (!props || !counts || (n && !aos)) return fail(IPIC_ERR_ARG, "null argument");
+	if (timesteps < 0 || frameInterval < 1 || numFrames < 1) return fail(IPIC_ERR_ARG, "bad tracer arguments (timesteps %d, frame interval %d, frames %d)", timesteps, frameInterval, numFrames);
+	if (timesteps > 0 && (timesteps - 1) / frameInterval >= numFrames) return fail(IPIC_ERR_ARG, "%d steps at one frame per %d steps need %d frames, %d offered", timesteps, frameInterval, (timesteps - 1) / frameInterval + 1, numFrames);
+	for (int a = 0; a < 3; a++) if (props->size[a] <= 0 || props->size[a] > 4096 || !(props->cellWidth[a] > 0)) return fail(IPIC_ERR_ARG, "bad grid");
+	if (!(props->dt > 0) || !(props->speedOfLight > 0) || !(props->planetRadius >= 0)) return fail(IPIC_ERR_ARG, "dt, speedOfLight must be positive and planetRadius non-negative");
+	int ndev = 0;
+	CK(cudaGetDeviceCount(&ndev));
+	if (device < 0 || device >= ndev) return fail(IPIC_ERR_CUDA, "CUDA device %d not available (%d devices)", device, ndev);
+	CK(cudaSetDevice(device));
+	ipic_ctx geo;                                      // only to derive the Geometry the kernels take
+	geo.props = *props;
+	fillGeometry(&geo);
+	const size_t cells = (size_t)numFrames * (size_t)geo.g.nx * geo.g.ny * geo.g.nz;
+	const uint64_t chunk = 1u << 22;                   // particles per upload: the next chunk crosses PCIe while this one is traced
+	unsigned* dCounts = nullptr;
+	double* dStage[2] = { nullptr, nullptr };
+	cudaStream_t st[2] = { nullptr, nullptr };
+	cudaEvent_t ev[2] = { nullptr, nullptr };
+	auto cleanup = [&]() { cudaFree(dCounts); for (int i = 0; i < 2; i++) { cudaFree(dStage[i]); if (st[i]) cudaStreamDestroy(st[i]); if (ev[i]) cudaEventDestroy(ev[i]); } };
+	#define TCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(IPIC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+	TCK(cudaMalloc(&dCounts, std::max<size_t>(cells, 1) * sizeof(unsigned)));
+	TCK(cudaMemset(dCounts, 0, std::max<size_t>(cells, 1) * sizeof(unsigned)));
+	for (int i = 0; i < 2; i++) {
+		TCK(cudaMalloc(&dStage[i], (size_t)std::min<uint64_t>(std::max<uint64_t>(n, 1), chunk) * 64));
+		TCK(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+		TCK(cudaEventCreate(&ev[i]));
+	}
+	TCK(cudaEventRecord(ev[0], st[0]));
+	int k = 0;
+	for (uint64_t first = 0; first < n; first += chunk, k ^= 1) {
+		const uint64_t cnt = std::min(chunk, n - first);
+		TCK(cudaMemcpyAsync(dStage[k], aos + first * 8, (size_t)cnt * 64, cudaMemcpyHostToDevice, st[k]));
+		launch_trace(geo.g, dStage[k], (int64_t)cnt, timesteps, frameInterval, dCounts, st[k]);
+	}
+	TCK(cudaStreamSynchronize(st[0]));
+	TCK(cudaStreamSynchronize(st[1]));
+	TCK(cudaEventRecord(ev[1], st[0]));
+	TCK(cudaEventSynchronize(ev[1]));
+	float ms = 0;
+	TCK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+	TCK(cudaGetLastError());
+	TCK(cudaMemcpy(counts, dCounts, cells * sizeof(unsigned), cudaMemcpyDeviceToHost));
+	#undef TCK
+	cleanup();
+	if (seconds) *seconds = ms / 1000.0;
 	return IPIC_OK;
 }
 

@@ -192,6 +192,25 @@ IPIC_API void ipic_mirror_get_fields(void* handle, double* field, double* bc, do
 	std::memcpy(J, u.currentDensity.data(), u.currentDensity.count() * sizeof(ipic3d::DensityNode));
 }
 
+// the particles pic_tracer's generator produces for one task (pic_tracer.cxx:236-262): seed = a*b of the task
+IPIC_API void ipic_mirror_tracer_particles(const ipic_props* props, uint32_t seed, uint64_t n, double* aos) {
+	using namespace ipic3d;
+	const Vector3<double> origin{ props->origin[0], props->origin[1], props->origin[2] };
+	const Vector3<double> width{ props->cellWidth[0], props->cellWidth[1], props->cellWidth[2] };
+	const coordinate_type size{ props->size[0], props->size[1], props->size[2] };
+	const double e = 1.602176565e-19, K = 1e7 * e, m = 1.672621777e-27;
+	const double v_mod = props->speedOfLight / std::sqrt(1.0 + (m * props->speedOfLight * props->speedOfLight) / K);
+	const auto low = origin + elementwiseProduct(width, size) / 8.0;
+	const auto hig = low + 0.75 * elementwiseProduct(width, size);
+	distribution::uniform_pos_normal_speed<> next(low, hig, Vector3<double>{ 0.0, 0.0, 0.0 }, Vector3<double>{ v_mod, v_mod, v_mod }, seed);
+	for (uint64_t i = 0; i < n; i++) {
+		Particle p = next();
+		p.q = e;
+		p.qom = e / m;
+		std::memcpy(aos + i * 8, &p, sizeof p);
+	}
+}
+
 // host folds of the conserved quantities (cell.h / field.h mirror): { momentum, E energy, B energy, KE }
 IPIC_API void ipic_mirror_diagnostics(void* handle, double* out4) {
 	using namespace ipic3d;

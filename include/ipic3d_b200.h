@@ -153,6 +153,16 @@ IPIC_API int  ipic_count_misplaced(ipic_ctx* ctx, uint64_t* misplaced);
 IPIC_API int  ipic_diagnostics(ipic_ctx* ctx, double* out4);
 IPIC_API int  ipic_group_diagnostics(ipic_ctx** ctxs, int n, double* out4);
 
+/* pic_tracer (code/app/src/pic_tracer.cxx:77-148, traceParticle): traces n independent particles (AoS records as
+ * above; the caller generates them, pic_tracer.cxx:236-262) for `timesteps` steps in the analytic dipole of `props`
+ * with periodic wrap-around and absorption by the planet, and counts each surviving particle into the density frame
+ * t / frame_interval at the cell it occupied before step t, every frame_interval steps.
+ * counts[num_frames][nx][ny][nz] (uint32, ParticleCount::flatten, pic_tracer.cxx:66-68) is overwritten.
+ * `seconds` (may be NULL): device time of upload + tracing.  No context needed; particles are streamed through
+ * the GPU in chunks, so n is not limited by HBM. */
+IPIC_API int  ipic_trace(const ipic_props* props, int device, const double* particles_aos, uint64_t n, int timesteps,
+                         int frame_interval, int num_frames, uint32_t* counts, double* seconds);
+
 /* Device self-test of the FP64 helpers that replace library code on the hot path (shared-reciprocal
  * division of the Boris rotation): number of random inputs (out of n) whose result is not bit-identical
  * to IEEE division.  Must be 0. */

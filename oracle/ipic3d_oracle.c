@@ -21,6 +21,7 @@
  *   orc_update_boundaries   <- updateFieldsOnBoundaries         hdr/field.h:407-440
  *   orc_init_fields         <- initFields/getDipoleFieldAt/initBcFields hdr/field.h:43-137
  *   orc_step                <- simulateSteps loop body          hdr/simulator.h:181-230
+ *   orc_trace               <- traceParticle                    code/app/src/pic_tracer.cxx:77-148
  *   orc_diagnostics         <- writeOutputData columns          hdr/simulator.h:71-91 (getFieldEnergy hdr/field.h:443-459,
  *                              getParticlesKineticEnergy / getParticlesMomentum / getTotalParticlesEnergy hdr/cell.h:1315-1355)
  *
@@ -205,6 +206,38 @@ int orc_move_particle_dipole(const ipic_props* P, double* p) {
 	B[1] = 3.0 * p[1] * p[2] * fac1;
 	B[2] = (2.0 * (p[2] * p[2]) - p[0] * p[0] - p[1] * p[1]) * fac1;
 	return push_with_fields(P, p, E, B);
+}
+
+/* pic_tracer.cxx:77-148: n independent particles, T steps, periodic wrap, absorption; counts[frame][x][y][z] += 1
+ * every frame_interval steps at the cell the particle occupied BEFORE that step's push.  The field expressions of
+ * pic_tracer.cxx:106-112 are those of cell.h:919-945 (pow(v, 2) == v * v exactly in glibc). */
+void orc_trace(const ipic_props* P, const double* aos, uint64_t n, int T, int frame_interval, uint32_t* counts) {
+	double usize[3], low[3], high[3];
+	for (int a = 0; a < 3; a++) { usize[a] = P->cellWidth[a] * (double)P->size[a]; low[a] = P->origin[a]; high[a] = P->origin[a] + usize[a]; }
+	const double R2 = P->planetRadius * P->planetRadius;
+	for (uint64_t i = 0; i < n; i++) {
+		double p[8];
+		memcpy(p, aos + i * 8, 64);
+		for (int a = 0; a < 3; a++) p[a] += P->objectCenter[a];
+		double r2 = 0.0; for (int a = 0; a < 3; a++) { double d = p[a] - P->objectCenter[a]; r2 += d * d; }
+		if (r2 < R2) continue;
+		int outside = 0;
+		for (int a = 0; a < 3; a++) if (p[a] > high[a] || p[a] < low[a]) outside = 1;
+		if (outside) continue;
+		for (int t = 0; t < T; t++) {
+			int64_t c[3];
+			for (int a = 0; a < 3; a++) c[a] = (int64_t)((p[a] - P->origin[a]) / P->cellWidth[a]);
+			orc_move_particle_dipole(P, p);
+			for (int a = 0; a < 3; a++) {
+				if (p[a] > high[a]) p[a] -= usize[a];
+				if (p[a] < low[a]) p[a] += usize[a];
+			}
+			r2 = 0.0; for (int a = 0; a < 3; a++) { double d = p[a] - P->objectCenter[a]; r2 += d * d; }
+			if (r2 <= R2) break;
+			if (t % frame_interval == 0 && c[0] >= 0 && c[0] < P->size[0] && c[1] >= 0 && c[1] < P->size[1] && c[2] >= 0 && c[2] < P->size[2])
+				counts[(((int64_t)(t / frame_interval) * P->size[0] + c[0]) * P->size[1] + c[1]) * P->size[2] + c[2]] += 1;
+		}
+	}
 }
 
 static void move_cell_dipole(orc_universe* u, plist* cell) {

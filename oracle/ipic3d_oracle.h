@@ -52,6 +52,9 @@ void orc_update_boundaries(orc_universe* u);
 /* mover for one particle in dipole-analytic mode; returns the number of sub-cycles used */
 int  orc_move_particle_dipole(const ipic_props* props, double* p8);
 
+/* pic_tracer's traceParticle over n particles (AoS); counts[frames][nx][ny][nz] is accumulated into */
+void orc_trace(const ipic_props* props, const double* aos, uint64_t n, int T, int frame_interval, uint32_t* counts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@
 namespace allscale { namespace api { namespace user { namespace algorithm {
 
 	namespace detail {
-		template<typename R> struct reduction_result { R value; R get() const { return value; } };
+		template<typename R> struct reduction_result { R value; R get() { return std::move(value); } };   // results may be move-only (pic_tracer's ParticleCount)
 	}
 
 	// range of grid points: fold(index, acc)
