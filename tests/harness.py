@@ -276,6 +276,14 @@ class Ref(_Universe):
         return cls(lib.ref_create_uniform(C.c_uint64(num_particles), C.byref(props)), props, lib)
 
     @classmethod
+    def benchmark(cls, kind, num_particles, threaded=False):
+        """Universe of the reference's ``:X:N`` benchmark, X in U (uniform), C (cluster), E (explosion), B (beam) (benchmark.h:81-138)."""
+        lib = cls.load(threaded)
+        lib.ref_create_benchmark.restype = C.c_void_p
+        props = Props()
+        return cls(lib.ref_create_benchmark(C.c_char(kind.encode()), C.c_uint64(num_particles), C.byref(props)), props, lib)
+
+    @classmethod
     def uniform_grid(cls, props, num_particles, threaded=False):
         lib = cls.load(threaded)
         props = props.copy()

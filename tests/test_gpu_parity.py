@@ -262,6 +262,26 @@ def test_uniform_benchmark_bit_exact_1m():
     assert bits_equal(aos, r.particles())
 
 
+@pytest.mark.parametrize("kind,n", [("C", 400000), ("E", 300000), ("B", 200000)])
+def test_nonuniform_benchmarks_bit_exact(kind, n):
+    """The reference's :C: cluster, :E: explosion and :B: beam benchmark universes (benchmark.h:94-138), 7 steps: counts
+    checked every step, every particle bit-exact at the end.  At this commit the reference's two-phase initCells
+    (cell.h:506-632) finds no pseudo-particle inside any cell for these generators and spreads the particles evenly, so
+    the loads start uniform in count; the beam (velocity = 6 cells per step, routed one cell per step) then piles up:
+    cells emptying and filling, particles outside their cell's box, segment re-layouts."""
+    if not Ref.available():
+        pytest.skip("oracle/_ref not built")
+    r = Ref.benchmark(kind, n, threaded=Ref.available(True))
+    counts0 = r.counts()
+    with ctx_for(r.props) as c:
+        c.upload_cells(counts0, r.particles())
+        for step in range(7):
+            c.step(1); r.step(1)
+            assert np.array_equal(c.cell_counts(), r.counts()), (kind, step)
+        counts, aos = c.download_cells()
+    assert bits_equal(aos, r.particles())
+
+
 def test_large_uniform_properties():
     """BASELINE size (32^3 cells, 16M particles), size-independent properties: particle number conserved,
     nobody misplaced, and ballistic motion is exactly invertible by negating velocities (no walls hit)."""
