@@ -61,6 +61,14 @@ struct ipic_ctx {
 	int* dStay = nullptr;                          // stayers per cell after the mover (head of segment, other generation)
 	int* dLeave = nullptr;                         // outbox entries per local cell
 	unsigned char* dTag = nullptr;                 // direction tag per slot (outbox entries only)
+	// chunked mover (k_move_chunk): chunk table of the current layout, ordered plane 0 | interior planes | last plane
+	bool chunked = false;                          // chosen at upload / re-layout from the populations (IPIC_CHUNKED=0/1 forces)
+	int2* dChunkTable = nullptr;
+	unsigned long long* dChunkStatus = nullptr;
+	unsigned* dChunkTicket = nullptr;              // [0] plane 0, [1] interior, [2] last plane, [3] whole slab
+	double* dChunkJ = nullptr;
+	int chunkRange[4] = { 0, 0, 0, 0 };            // table offsets: plane 0 = [r0, r1), interior = [r1, r2), last plane = [r2, r3)
+	int64_t chunkCapacity = 0;                     // chunks the device arrays were allocated for
 	int* dStop = nullptr;                          // [0] stop, [1] first failing step, [2] cell overflow seen in this import pass, [3] exchange failure (1 face message full on this rank, 2 unusable message received)
 	bool haveCells = false;
 	int64_t meanPopulation = 0;                    // particles per owned cell at upload (drives the mover's tile shape)
@@ -145,6 +153,45 @@ void buildLayout(const ipic_ctx* c, const std::vector<int64_t>& need, std::vecto
 	int64_t pos = 0;
 	for (int cell = 0; cell < g.ncellsLocal; cell++) { start[(size_t)cell] = pos; pos += capacityFor(c, need[(size_t)cell]); }
 	start[(size_t)g.ncellsLocal] = pos;
+}
+
+// Chunk table of the layout in c->hCellStart, and the choice between one CTA per cell (k_move) and several
+// (k_move_chunk): the latter when cells are big enough that whole cells are too few / too uneven work items.
+int buildChunkTable(ipic_ctx* c, int64_t maxPopulation) {
+	const Geometry& g = c->g;
+	const int per = chunk_particles();
+	c->chunked = maxPopulation > 4 * (int64_t)per;
+	if (const char* e = std::getenv("IPIC_CHUNKED")) c->chunked = std::atoi(e) != 0;
+	if (!c->chunked) return IPIC_OK;
+	std::vector<int2> table;
+	auto addPlanes = [&](int zFirst, int zEnd) {
+		for (int xy = 0; xy < g.nx * g.ny; xy++) for (int zl = zFirst; zl < zEnd; zl++) {
+			const int cell = xy * g.lz + zl;
+			const int64_t cap = c->hCellStart[(size_t)cell + 1] - c->hCellStart[(size_t)cell];
+			const int nch = (int)std::max<int64_t>(1, (cap + per - 1) / per);
+			for (int j = 0; j < nch; j++) table.push_back(make_int2(cell, j));
+		}
+	};
+	c->chunkRange[0] = 0;
+	addPlanes(0, std::min(1, g.lz));
+	c->chunkRange[1] = (int)table.size();
+	addPlanes(1, std::max(1, g.lz - 1));
+	c->chunkRange[2] = (int)table.size();
+	if (g.lz > 1) addPlanes(g.lz - 1, g.lz);
+	c->chunkRange[3] = (int)table.size();
+	if ((int64_t)table.size() > c->chunkCapacity) {
+		cudaFree(c->dChunkTable); cudaFree(c->dChunkStatus); cudaFree(c->dChunkJ);
+		c->dChunkTable = nullptr; c->dChunkStatus = nullptr; c->dChunkJ = nullptr; c->chunkCapacity = 0;
+		const size_t cap = table.size() + table.size() / 4;
+		CK(cudaMalloc(&c->dChunkTable, cap * sizeof(int2)));
+		CK(cudaMalloc(&c->dChunkStatus, cap * sizeof(unsigned long long)));
+		CK(cudaMalloc(&c->dChunkJ, cap * 24 * sizeof(double)));
+		c->chunkCapacity = (int64_t)cap;
+	}
+	if (!c->dChunkTicket) CK(cudaMalloc(&c->dChunkTicket, 4 * sizeof(unsigned)));
+	CK(cudaMemcpyAsync(c->dChunkTable, table.data(), table.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return IPIC_OK;
 }
 
 int ensureStage(ipic_ctx* c, int64_t doubles) {
@@ -283,7 +330,7 @@ int relayoutAfterOverflow(ipic_ctx* c, int outGen, int failedStep) {
 	cudaFree(c->dCellStart);
 	c->buf[0] = nb[0]; c->buf[1] = nb[1]; c->dTag = ntag; c->dCellStart = dNewStart; c->slots = nslots; c->slotsNf = c->g.nf; c->hCellStart = newStart;
 	if (stop[0]) return fail(IPIC_ERR_INTERNAL, "relayout did not resolve the overflow of step %d", failedStep);
-	return IPIC_OK;
+	return buildChunkTable(c, *std::max_element(need64.begin(), need64.end()));
 }
 
 // Leave the uniform-species layout: same segments, 8 fields per particle, q and qom materialised.  Needed when
@@ -416,6 +463,7 @@ int ipic_destroy(ipic_ctx* c) {
 	if (c->bStream) cudaStreamDestroy(c->bStream);
 	freeParticleBuffers(c);
 	cudaFree(c->dCellStart); cudaFree(c->dCount); cudaFree(c->dStay); cudaFree(c->dLeave); cudaFree(c->dStop);
+	cudaFree(c->dChunkTable); cudaFree(c->dChunkStatus); cudaFree(c->dChunkTicket); cudaFree(c->dChunkJ);
 	cudaFree(c->dEB); cudaFree(c->dBext); cudaFree(c->dBc); cudaFree(c->dJ); cudaFree(c->dCellJ);
 	cudaFree(c->dStage); cudaFree(c->dAosStart);
 	for (auto e : c->events) cudaEventDestroy(e);
@@ -492,6 +540,8 @@ int ipic_upload_cells(ipic_ctx* c, const uint64_t* counts, const double* aos) {
 		c->slotsNf = nf;
 	}
 	c->hCellStart = start;
+	rc = buildChunkTable(c, need.empty() ? 0 : *std::max_element(need.begin(), need.end()));
+	if (rc) return rc;
 	CK(cudaMemcpyAsync(c->dCellStart, start.data(), start.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
 	CK(cudaMemcpyAsync(c->dAosStart, aosStart.data(), aosStart.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
 	CK(cudaMemcpyAsync(c->dCount, localCount.data(), localCount.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -617,6 +667,22 @@ MoveArgs moveArgs(ipic_ctx* c, const StepFlags& f, int zBegin, int zCount) {
 	ma.zBegin = zBegin; ma.zCount = zCount;
 	ma.interpolate = f.interp; ma.migrate = f.migrate; ma.push = true; ma.deposit = f.fuseDeposit;
 	pickTileShape(c, ma.deposit, ma.stages);
+	ma.chunked = false;
+	if (c->chunked) {
+		const int lz = c->g.lz;
+		int grp = -1;
+		if (zBegin == 0 && zCount == lz) grp = 3;
+		else if (zBegin == 0 && zCount == 1) grp = 0;
+		else if (zBegin == lz - 1 && zCount == 1) grp = 2;
+		else if (zBegin == 1 && zCount == lz - 2) grp = 1;
+		if (grp >= 0) {
+			ma.chunked = true;
+			ma.chunkTable = c->dChunkTable; ma.chunkStatus = c->dChunkStatus; ma.chunkJ = c->dChunkJ;
+			ma.chunkTicket = c->dChunkTicket + grp;
+			ma.chunkFirst = grp == 3 ? 0 : c->chunkRange[grp];
+			ma.chunkCount = (grp == 3 ? c->chunkRange[3] : c->chunkRange[grp + 1]) - ma.chunkFirst;
+		}
+	}
 	return ma;
 }
 

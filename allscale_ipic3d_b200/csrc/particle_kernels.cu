@@ -20,6 +20,12 @@ namespace ipic {
 
 constexpr int kBlock = 128;                 // threads per CTA of the mover (one CTA per cell)
 constexpr int kWarps = kBlock / 32;
+#ifndef IPIC_CHUNK_ITERS
+#define IPIC_CHUNK_ITERS 4           // chunk = 4 x 128 = 512 particles (24 KiB of shared memory in the one-species layout)
+#endif
+#ifndef IPIC_CHUNK_MINB
+#define IPIC_CHUNK_MINB 5
+#endif
 constexpr int kRedRow = 16 * 9 + 8;          // padded row of the deposit reduction buffer (doubles): 16 segments of 8 (+1)
 
 // ---- TMA (bulk async copy) helpers: global -> shared, completion on an mbarrier ------------------
@@ -312,6 +318,283 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	}
 	if (PUSH && tid == 0) { countOut[cell] = kept; nLeave[cell] = left; }
 	if (DEPOSIT && tid < 24) cellJ[cellj_index(g, cx, cy, cz) + tid] = sJ[tid];      // GLOBAL cell id, z-major: a slab is contiguous
+}
+
+// ---- chunked mover: several CTAs per cell ----------------------------------------------------------
+//
+// k_move gives a cell to ONE CTA, which is the right shape while cells hold a few hundred to a few thousand
+// particles.  When cells are large (weak scaling on a fixed grid: 7812 particles per cell at 8 GPUs, so only 4096
+// work items per slab) or very uneven (the reference's :E: / :B: loads pile most of the plasma into a few cells)
+// that serialises the work.  k_move_chunk splits every cell segment into chunks of kChunk slots, one CTA each:
+//
+//   1. the chunk (<= kChunk particles, one contiguous piece of HBM) is brought into shared memory by ONE TMA bulk copy;
+//   2. deposit (pre-push state, 24 corner sums -> block reduction), then push + classify IN PLACE in shared memory;
+//      per 32-particle block the numbers of stayers / leavers (ballots) are kept, and scanned over the chunk;
+//   3. a cell with several chunks needs, for a stable compaction, the totals of the chunks before this one: a
+//      single-pass chained scan with decoupled look-back over one 64-bit status word per chunk
+//      (flag | stayers | leavers).  Chunks are handed out through a ticket counter, so every predecessor of a
+//      running chunk is itself running or done -- the look-back cannot wait for a CTA that was never scheduled;
+//   4. the chunk is written out of shared memory: stayers to the head of the cell's segment at (prefix + offset),
+//      leavers backwards into the outbox at the tail, exactly where the one-CTA kernel puts them.
+//
+// Results (particle order, counts, tags) are identical to k_move's; the per-cell corner sums of the deposit are
+// the chunk partials added in chunk order by the cell's last chunk.
+
+constexpr int kChunkIters = IPIC_CHUNK_ITERS;      // 32-particle blocks per warp and chunk
+constexpr int kChunk = kChunkIters * kBlock;       // particles per chunk
+constexpr int kChunkBlocks = kChunk / 32;
+
+#define kStatusAggregate (1ull << 62)
+#define kStatusPrefix (2ull << 62)
+#define kStatusMask (3ull << 62)
+__device__ __forceinline__ unsigned long long pack_status(unsigned long long flag, unsigned stay, unsigned leave) {
+	return flag | ((unsigned long long)stay << 31) | (unsigned long long)leave;
+}
+__device__ __forceinline__ unsigned status_stay(unsigned long long w) { return (unsigned)((w >> 31) & 0x7fffffffu); }
+__device__ __forceinline__ unsigned status_leave(unsigned long long w) { return (unsigned)(w & 0x7fffffffu); }
+
+template<int NF, bool INTERP, bool DEPOSIT, bool MIGRATE>
+__global__ void __launch_bounds__(kBlock, IPIC_CHUNK_MINB)
+k_move_chunk(const Geometry g, const ParticleArrays in, const ParticleArrays out, const int64_t* __restrict__ cellStart,
+             const int* __restrict__ countIn, int* __restrict__ countOut, int* __restrict__ nLeave,
+             unsigned char* __restrict__ tag, const double* __restrict__ fieldEB, double* __restrict__ cellJ, double* chunkJ,
+             const int* __restrict__ stopFlag, const int2* __restrict__ chunkTable, int rangeStart, unsigned* ticket,
+             unsigned long long* status) {
+
+	constexpr int BLOCK_DOUBLES = 32 * NF;
+	if (*stopFlag) return;
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	extern __shared__ __align__(128) double sTile[];             // kChunk x NF doubles, AoSoA blocks as in HBM
+	__shared__ uint64_t sFull, sBar;
+	__shared__ int sPos;
+	__shared__ unsigned char sCode[kChunk];
+	__shared__ int sBlk[kChunkBlocks];                           // per 32-particle block: stayers | leavers << 16
+	__shared__ int sOff[2][kChunkBlocks];                        // exclusive scans over the blocks: [0] stayers, [1] leavers
+	__shared__ int sPrefix[2];                                   // stayers / leavers of the cell's earlier chunks
+	__shared__ alignas(16) double sCorner[48];
+	__shared__ double sRed[DEPOSIT ? 8 * kRedRow : 1];
+	__shared__ double sJ[24];
+	__shared__ double sGeo[6];
+
+	if (tid == 0) sPos = rangeStart + (int)atomicAdd(ticket, 1u);
+	__syncthreads();
+	const int pos = sPos;
+	const int2 ref = chunkTable[pos];
+	const int cell = ref.x, j = ref.y;
+	const int xy = cell / g.lz, zl = cell - xy * g.lz;
+	const int cx = xy / g.ny, cy = xy - cx * g.ny, cz = g.z0 + zl;
+
+	const int n = countIn[cell];
+	const int lo = j * kChunk;
+	const int cnt = min(kChunk, n - lo);
+	if (cnt <= 0 && !(j == 0 && n == 0)) return;                 // chunk beyond the population: nobody waits for it
+	const bool last = lo + kChunk >= n;                          // the cell's last populated chunk
+	const int64_t base = cellStart[cell];
+	const int cap = (int)(cellStart[cell + 1] - base);
+	double* __restrict__ dst = out.d + base * NF;
+
+	if (tid >= 32 && tid < 35) {
+		const int a = tid - 32;
+		const int cc = a == 0 ? cx : (a == 1 ? cy : cz);
+		const double o = g.origin[a] + (double)cc * g.w[a];
+		sGeo[a] = o;
+		sGeo[3 + a] = o + g.hw[a];
+	}
+	if (tid == 0) {
+		mbar_init(&sFull, 1);
+		if (INTERP) mbar_init(&sBar, 1);
+	}
+	__syncthreads();
+	if (tid == 0 && cnt > 0) {
+		const uint32_t bytes = (uint32_t)((cnt + 31) >> 5) * (BLOCK_DOUBLES * 8);
+		mbar_expect_tx(&sFull, bytes);
+		tma_bulk_g2s(sTile, in.d + (base + lo) * NF, bytes, &sFull);
+		if (INTERP) {
+			mbar_expect_tx(&sBar, 4 * 96);
+			const int fy = g.ny + 3, fz = g.nz + 3;
+			#pragma unroll
+			for (int i = 0; i < 2; i++)
+				#pragma unroll
+				for (int jj = 0; jj < 2; jj++) {
+					const int64_t node = ((int64_t)(cx + i + 1) * fy + (cy + jj + 1)) * fz + (cz + 1);
+					tma_bulk_g2s(&sCorner[(i * 2 + jj) * 12], fieldEB + node * 6, 96, &sBar);
+				}
+		}
+	}
+	const double* org = sGeo;
+	const double* ctr = sGeo + 3;
+	const bool wallCell = cx == 0 || cy == 0 || cz == 0 || cx == g.nx - 1 || cy == g.ny - 1 || cz == g.nz - 1;
+	const bool fieldFree = !INTERP && g.magTemp == 0.0 && g.pic > 0.0 && g.dt > 0.0 && g.dt < 1e100;
+	const unsigned lt = (1u << lane) - 1u;
+
+	if (cnt > 0) {
+		if (INTERP) mbar_wait(&sBar, 0);
+		mbar_wait(&sFull, 0);
+	}
+
+	if (DEPOSIT) {
+		double acc[24];
+		#pragma unroll
+		for (int a = 0; a < 24; a++) acc[a] = 0.0;
+		for (int it = 0; it < kChunkIters; it++) {
+			const int idx = it * kBlock + tid;
+			if (idx < cnt) {
+				const double* p = sTile + (it * kWarps + warp) * BLOCK_DOUBLES + lane;
+				const double rx = (p[0] - org[0]) * g.iw[0], ry = (p[32] - org[1]) * g.iw[1], rz = (p[64] - org[2]) * g.iw[2];
+				const double ox = 1.0 - rx, oy = 1.0 - ry, oz = 1.0 - rz;
+				const double q = NF == 8 ? p[192] : g.uq;
+				const double jx = q * p[96], jy = q * p[128], jz = q * p[160];
+				const double wxy[4] = { ox * oy, ox * ry, rx * oy, rx * ry };
+				#pragma unroll
+				for (int ab = 0; ab < 4; ab++) {
+					const double f0 = wxy[ab] * oz, f1 = wxy[ab] * rz;
+					const int o = ab * 6;
+					acc[o] = __fma_rn(jx, f0, acc[o]); acc[o + 1] = __fma_rn(jy, f0, acc[o + 1]); acc[o + 2] = __fma_rn(jz, f0, acc[o + 2]);
+					acc[o + 3] = __fma_rn(jx, f1, acc[o + 3]); acc[o + 4] = __fma_rn(jy, f1, acc[o + 4]); acc[o + 5] = __fma_rn(jz, f1, acc[o + 5]);
+				}
+			}
+		}
+		#pragma unroll
+		for (int pass = 0; pass < 3; pass++) {
+			#pragma unroll
+			for (int r = 0; r < 8; r++) sRed[r * kRedRow + (tid >> 3) * 9 + (tid & 7)] = acc[pass * 8 + r];
+			__syncthreads();
+			{
+				const int row = tid >> 4, seg = tid & 15;
+				const double* r = sRed + row * kRedRow + seg * 9;
+				double v = r[0];
+				#pragma unroll
+				for (int i = 1; i < 8; i++) v += r[i];
+				v += __shfl_xor_sync(0xffffffffu, v, 1);
+				v += __shfl_xor_sync(0xffffffffu, v, 2);
+				v += __shfl_xor_sync(0xffffffffu, v, 4);
+				v += __shfl_xor_sync(0xffffffffu, v, 8);
+				if (seg == 0) sJ[pass * 8 + row] = v;
+			}
+			__syncthreads();
+		}
+		// a cell of several chunks: park the partial where the cell's last chunk will find it (visible before the status word)
+		if (n > kChunk && tid < 24) { chunkJ[(int64_t)pos * 24 + tid] = sJ[tid]; __threadfence(); }
+	}
+
+	// ---- push + classify in place; per-block counts ---------------------------------------------
+	for (int it = 0; it < kChunkIters; it++) {
+		const int idx = it * kBlock + tid;
+		unsigned code = kTagNone;
+		if (idx < cnt) {
+			double* p = sTile + (it * kWarps + warp) * BLOCK_DOUBLES + lane;
+			double px = p[0], py = p[32], pz = p[64], vx = p[96], vy = p[128], vz = p[160];
+			const double pm = NF == 8 ? p[224] : g.uqom;
+			if (INTERP) {
+				const double rx = (px - org[0]) / g.w[0], ry = (py - org[1]) / g.w[1], rz = (pz - org[2]) / g.w[2];
+				const Vec3 E = trilinear(sCorner, 6, rx, ry, rz, g.vol);
+				const Vec3 B = trilinear(sCorner + 3, 6, rx, ry, rz, g.vol);
+				push_with_fields(g, px, py, pz, vx, vy, vz, pm, E, B);
+			} else if (!(fieldFree && field_free_push(g, px, py, pz, vx, vy, vz, pm))) {
+				Vec3 E, B;
+				dipole_field(g, px, py, pz, E, B);
+				push_with_fields(g, px, py, pz, vx, vy, vz, pm, E, B);
+			}
+			code = MIGRATE ? classify(g, wallCell, cx, cy, cz, ctr, px, py, pz, vx, vy, vz) : 13u;
+			p[0] = px; p[32] = py; p[64] = pz; p[96] = vx; p[128] = vy; p[160] = vz;
+		}
+		if (idx < kChunk) sCode[idx] = (unsigned char)code;
+		const unsigned bs = __ballot_sync(0xffffffffu, code == 13u);
+		const unsigned bl = __ballot_sync(0xffffffffu, code < 27u && code != 13u);
+		if (lane == 0) sBlk[it * kWarps + warp] = __popc(bs) | (__popc(bl) << 16);
+	}
+	__syncthreads();
+
+	// ---- scan over the chunk's blocks, then the cell-level prefix (look-back) ----------------------
+	if (warp == 0) {
+		unsigned totS = 0, totL = 0;
+		#pragma unroll
+		for (int b0 = 0; b0 < kChunkBlocks; b0 += 32) {
+			const int v = (b0 + lane < kChunkBlocks) ? sBlk[b0 + lane] : 0;
+			int s = v & 0xffff, l = v >> 16;
+			int is = s, il = l;
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const int ts = __shfl_up_sync(0xffffffffu, is, d), tl = __shfl_up_sync(0xffffffffu, il, d);
+				if (lane >= d) { is += ts; il += tl; }
+			}
+			if (b0 + lane < kChunkBlocks) { sOff[0][b0 + lane] = (int)totS + is - s; sOff[1][b0 + lane] = (int)totL + il - l; }
+			totS += (unsigned)__shfl_sync(0xffffffffu, is, 31);
+			totL += (unsigned)__shfl_sync(0xffffffffu, il, 31);
+		}
+		unsigned preS = 0, preL = 0;
+		if (n > kChunk) {
+			volatile unsigned long long* st = status;
+			if (!last && lane == 0) st[pos] = pack_status(j == 0 ? kStatusPrefix : kStatusAggregate, totS, totL);
+			int remaining = j, look = pos - 1;
+			while (remaining > 0) {
+				const int k = min(32, remaining);
+				unsigned long long w;
+				do { w = lane < k ? st[look - lane] : kStatusPrefix; } while (__any_sync(0xffffffffu, (w & kStatusMask) == 0));
+				const unsigned pm = __ballot_sync(0xffffffffu, lane < k && (w & kStatusMask) == kStatusPrefix);
+				const int stopLane = pm ? __ffs(pm) - 1 : k - 1;          // nearest predecessor that already knows its inclusive prefix
+				const unsigned s = lane <= stopLane ? status_stay(w) : 0u, l = lane <= stopLane ? status_leave(w) : 0u;
+				preS += __reduce_add_sync(0xffffffffu, s);
+				preL += __reduce_add_sync(0xffffffffu, l);
+				if (pm) break;
+				look -= k; remaining -= k;
+			}
+			if (!last && j > 0 && lane == 0) st[pos] = pack_status(kStatusPrefix, preS + totS, preL + totL);
+			__threadfence();                                             // the predecessors' deposit partials are read after their status words
+		}
+		if (lane == 0) {
+			sPrefix[0] = (int)preS; sPrefix[1] = (int)preL;
+			if (last) { countOut[cell] = (int)(preS + totS); nLeave[cell] = (int)(preL + totL); }
+		}
+	}
+	__syncthreads();
+
+	// ---- write-out from shared memory --------------------------------------------------------------
+	const int preS = sPrefix[0], preL = sPrefix[1];
+	for (int it = 0; it < kChunkIters; it++) {
+		const int idx = it * kBlock + tid;
+		const unsigned code = idx < kChunk ? sCode[idx] : kTagNone;
+		const bool stay = code == 13u, leave = code < 27u && code != 13u;
+		const unsigned bs = __ballot_sync(0xffffffffu, stay), bl = __ballot_sync(0xffffffffu, leave);
+		if (stay || leave) {
+			const int blk = it * kWarps + warp;
+			int d;
+			if (stay) d = preS + sOff[0][blk] + __popc(bs & lt);
+			else {
+				d = cap - 1 - (preL + sOff[1][blk] + __popc(bl & lt));
+				tag[base + d] = (unsigned char)code;
+			}
+			const double* p = sTile + blk * BLOCK_DOUBLES + lane;
+			double* q = dst + (int64_t)(d >> 5) * BLOCK_DOUBLES + (d & 31);
+			st_stream(q, p[0]); st_stream(q + 32, p[32]); st_stream(q + 64, p[64]);
+			st_stream(q + 96, p[96]); st_stream(q + 128, p[128]); st_stream(q + 160, p[160]);
+			if (NF == 8) { st_stream(q + 192, p[192]); st_stream(q + 224, p[224]); }
+		}
+	}
+
+	if (DEPOSIT) {
+		if (n <= kChunk) {
+			if (tid < 24) cellJ[cellj_index(g, cx, cy, cz) + tid] = sJ[tid];
+		} else if (last) {
+			// every earlier chunk has published a status word by now (look-back), hence its partial: add them in chunk
+			// order; 5 strided partial sums per component, combined in fixed order
+			__shared__ double sSum[5][24];
+			const int grp = tid / 24, comp = tid - grp * 24;
+			if (grp < 5) {
+				double v = 0.0;
+				for (int k = grp; k < j; k += 5) v += __ldcg(chunkJ + (int64_t)(pos - j + k) * 24 + comp);
+				sSum[grp][comp] = v;
+			}
+			__syncthreads();
+			if (tid < 24) {
+				double v = sSum[0][tid];
+				#pragma unroll
+				for (int k = 1; k < 5; k++) v += sSum[k][tid];
+				cellJ[cellj_index(g, cx, cy, cz) + tid] = v + sJ[tid];
+			}
+		}
+	}
 }
 
 // ---- import: append the 26 incoming outboxes in canonical order (reference cell.h:1195-1310) ------
@@ -760,7 +1043,38 @@ static void launch_move_i(const MoveArgs& a, cudaStream_t st) {
 	else { if (a.deposit) launch_move_t<NF, false, true>(a, st); else launch_move_t<NF, false, false>(a, st); }
 }
 
+template<int NF, bool INTERP, bool DEPOSIT, bool MIGRATE>
+static void launch_chunk_k(const MoveArgs& a, cudaStream_t st) {
+	static bool configured = false;
+	auto kernel = k_move_chunk<NF, INTERP, DEPOSIT, MIGRATE>;
+	const size_t smem = (size_t)kChunk * NF * sizeof(double);
+	if (!configured) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+	cudaMemsetAsync(a.chunkStatus + a.chunkFirst, 0, (size_t)a.chunkCount * sizeof(unsigned long long), st);
+	cudaMemsetAsync(a.chunkTicket, 0, sizeof(unsigned), st);
+	kernel<<<a.chunkCount, kBlock, smem, st>>>(a.g, a.in, a.out, a.cellStart, a.countIn, a.countOut, a.nLeave, a.tag, a.fieldEB, a.cellJ, a.chunkJ,
+	                                          a.stopFlag, a.chunkTable, a.chunkFirst, a.chunkTicket, a.chunkStatus);
+}
+
+template<int NF>
+static void launch_chunk_i(const MoveArgs& a, cudaStream_t st) {
+	if (a.interpolate) {
+		if (a.deposit) { if (a.migrate) launch_chunk_k<NF, true, true, true>(a, st); else launch_chunk_k<NF, true, true, false>(a, st); }
+		else { if (a.migrate) launch_chunk_k<NF, true, false, true>(a, st); else launch_chunk_k<NF, true, false, false>(a, st); }
+	} else {
+		if (a.deposit) { if (a.migrate) launch_chunk_k<NF, false, true, true>(a, st); else launch_chunk_k<NF, false, true, false>(a, st); }
+		else { if (a.migrate) launch_chunk_k<NF, false, false, true>(a, st); else launch_chunk_k<NF, false, false, false>(a, st); }
+	}
+}
+
+int chunk_particles() { return kChunk; }
+
 void launch_move(const MoveArgs& a, cudaStream_t st) {
+	if (a.chunked && a.push) {
+		if (a.chunkCount <= 0) return;
+		if (a.g.nf == 6) launch_chunk_i<6>(a, st);
+		else launch_chunk_i<8>(a, st);
+		return;
+	}
 	if (a.g.nf == 6) launch_move_i<6>(a, st);
 	else launch_move_i<8>(a, st);
 }

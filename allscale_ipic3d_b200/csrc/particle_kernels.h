@@ -18,7 +18,17 @@ struct MoveArgs {
 	int zBegin, zCount;        // owned z-planes [zBegin, zBegin+zCount) of the slab
 	int stages;                // shared-memory tile stages per CTA (TMA ring)
 	bool interpolate, deposit, migrate, push;   // push=false: deposit-only pass (no write-back)
+	// chunked mover (several CTAs per cell, k_move_chunk): the chunks [chunkFirst, chunkFirst + chunkCount) of the table
+	bool chunked;
+	const int2* chunkTable;    // per chunk: (local cell id, index of the chunk within the cell)
+	int chunkFirst, chunkCount;
+	unsigned* chunkTicket;     // hands the chunks out in table order
+	unsigned long long* chunkStatus;   // one look-back word per chunk
+	double* chunkJ;            // 24 deposit partials per chunk (cells of several chunks)
 };
+
+// particles per chunk of the chunked mover
+int chunk_particles();
 
 struct ImportArgs {
 	Geometry g;
