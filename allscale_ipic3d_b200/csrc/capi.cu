@@ -74,6 +74,9 @@ struct ipic_ctx {
 	int64_t meanPopulation = 0;                    // particles per owned cell at upload (drives the mover's tile shape)
 	double slack = 0.25;                           // head-room per cell as a fraction of its population
 	int64_t minPad = 64;                           // ... and in absolute slots
+	int64_t padFloor = 0;                          // adaptive absolute head-room: a share of the MEAN population, for universes whose sparse
+	                                               // cells fill up (dipole runs start with 12 particles in the outer cells); doubles per re-layout
+	bool userHeadroom = false;                     // ipic_set_headroom was called: no automatic floor at upload
 
 	// fields (always the global grids; replicated per slab)
 	double* dEB = nullptr;                         // (n+3)^3 x 6
@@ -143,7 +146,7 @@ int allocParticleBuffers(ParticleArrays out[2], unsigned char** tag, int64_t slo
 
 // capacity of a cell segment that currently needs room for n particles
 int64_t capacityFor(const ipic_ctx* c, int64_t n) {
-	return alignUp(n + std::max<int64_t>((int64_t)std::ceil((double)n * c->slack), c->minPad), kSlotAlign);
+	return alignUp(n + std::max<int64_t>(std::max<int64_t>((int64_t)std::ceil((double)n * c->slack), c->minPad), c->padFloor), kSlotAlign);
 }
 
 // segment layout of the slab's cells: capacity for the current population plus head-room
@@ -160,7 +163,10 @@ void buildLayout(const ipic_ctx* c, const std::vector<int64_t>& need, std::vecto
 int buildChunkTable(ipic_ctx* c, int64_t maxPopulation) {
 	const Geometry& g = c->g;
 	const int per = chunk_particles();
-	c->chunked = maxPopulation > 4 * (int64_t)per;
+	// measured on B200 (scripts/probe_loads.py): one CTA per cell wins up to ~50 k particles in the fullest cell (k_move
+	// 0.36 ms vs 0.43 ms on the :E: load); beyond that a single CTA becomes the critical path (:B: load, 6.5 M particles in
+	// one cell: 28.8 ms vs 0.59 ms chunked)
+	c->chunked = maxPopulation > 128 * (int64_t)per;
 	if (const char* e = std::getenv("IPIC_CHUNKED")) c->chunked = std::atoi(e) != 0;
 	if (!c->chunked) return IPIC_OK;
 	std::vector<int2> table;
@@ -303,6 +309,12 @@ int relayoutAfterOverflow(ipic_ctx* c, int outGen, int failedStep) {
 	std::vector<int64_t> need64(need.begin(), need.end());
 	std::vector<int64_t> newStart;
 	c->slack = std::min(c->slack * 1.5 + 0.1, 4.0);
+	{
+		int64_t total = 0;
+		for (int64_t v : need64) total += v;
+		const int64_t mean = total / std::max<int64_t>(1, (int64_t)need64.size());
+		c->padFloor = std::min<int64_t>(std::max<int64_t>(2 * c->padFloor, mean / 4), 2 * mean + 64);
+	}
 	buildLayout(c, need64, newStart);
 	ParticleArrays nb[2]{}; unsigned char* ntag = nullptr;
 	const int64_t nslots = newStart.back();
@@ -475,6 +487,7 @@ int ipic_destroy(ipic_ctx* c) {
 int ipic_set_headroom(ipic_ctx* c, double slack, int64_t minPad) {
 	if (!c || !(slack >= 0) || minPad < 0) return fail(IPIC_ERR_ARG, "bad head-room");
 	c->slack = slack; c->minPad = minPad;
+	c->userHeadroom = true; c->padFloor = 0;
 	return IPIC_OK;
 }
 
@@ -530,6 +543,14 @@ int ipic_upload_cells(ipic_ctx* c, const uint64_t* counts, const double* aos) {
 		}
 	}
 	c->g.nf = nf; c->g.uq = uq; c->g.uqom = uqom;
+	if (!c->userHeadroom) {
+		// sparse cells next to full ones fill up towards the mean (the dipole runs start with 12 particles per cell outside the
+		// inner box and ~1000 inside; diffusion levels that out): give every cell room for the mean population and a quarter,
+		// instead of paying a re-layout every few steps.  Evenly filled universes (:U:) keep the tight layout.
+		const int64_t mean = total / std::max(1, nOwned);
+		const int64_t least = need.empty() ? 0 : *std::min_element(need.begin(), need.end());
+		c->padFloor = least < mean / 4 ? mean + mean / 4 : 0;
+	}
 	std::vector<int64_t> start;
 	buildLayout(c, need, start);
 	if (start.back() > c->slots || start.back() < c->slots / 2 || c->slotsNf != nf) {

@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--grid", type=int, default=32)
     ap.add_argument("--no-deposit", action="store_true", help="time the loop as the reference ships it (STEP 1 off)")
     ap.add_argument("--workload", default="uniform", choices=["uniform", "dipole"],
-                    help="uniform = the headline :U:N plasma; dipole = a secondary, single-GPU data point: the reference's Earth-dipole "
+                    help="uniform = the headline :U:N plasma; dipole = a secondary data point (fixed total, z-slabs over the ranks): the reference's Earth-dipole "
                          ".inp set-up (medium.inp physics: 0.625 R_E cells, 10 MeV protons, absorption, ~17 %% migration per step) on --grid^3 "
                          "cells with 8^3 particles per cell")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -202,11 +202,17 @@ def run_b200(args):
         raise SystemExit("grid z extent %d not divisible by %d ranks" % (nz, world))
     lz = nz // world
     if args.workload == "dipole":
-        if world != 1:
-            raise SystemExit("--workload dipole is a single-GPU data point")
+        # every rank builds the whole universe (host mirror generator) and keeps its z-slab; the total is fixed: strong scaling
         props, counts, aos = capi.dipole_universe(os.path.join(ROOT, "tests", "golden", "inputs", "medium.inp"), args.grid, 8)
-        n_total = n_local = int(counts.sum())
-        host = torch.from_numpy(aos).pin_memory()
+        n_total = int(counts.sum())
+        if world > 1:
+            first = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+            cells = (np.arange(nz * nz)[:, None] * nz + rank * lz + np.arange(lz)[None, :]).reshape(-1)    # slab order (x*ny + y)*lz + zl
+            counts = counts[cells]
+            idx = np.repeat(first[cells] - np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64), counts.astype(np.int64)) + np.arange(int(counts.sum()))
+            aos = aos[idx]
+        n_local = int(counts.sum())
+        host = torch.from_numpy(np.ascontiguousarray(aos)).pin_memory()
         del aos
     else:
         props = capi.uniform_benchmark_props(args.grid)
@@ -308,7 +314,7 @@ def run_b200(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": seconds / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": seconds / args.steps * 1e3, "higher_is_better": True, "scaling": "weak" if args.workload == "uniform" else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": ("uniform plasma :U:N (reference generator, bit-identical), %dx%dx%d cells, %d particles per GPU, z-slabs"
                                     % (args.grid, args.grid, args.grid, args.particles_per_gpu)) if args.workload == "uniform" else
