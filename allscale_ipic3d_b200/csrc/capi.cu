@@ -247,7 +247,8 @@ void fillGeometry(ipic_ctx* c) {
 void pickTileShape(const ipic_ctx* c, bool deposit, int& stages) {
 	const int64_t avg = c->meanPopulation;
 	const int64_t tile = 128;
-	stages = (int)std::max<int64_t>(1, std::min<int64_t>((avg + avg / 8 + tile - 1) / tile, deposit ? 4 : 2));
+	// fused deposit, warp-specialised (k_move_ws): a deep ring decouples the deposit warp from the push warps (sweep: 8 > 6 > 4)
+	stages = (int)std::max<int64_t>(1, std::min<int64_t>((avg + avg / 8 + tile - 1) / tile, deposit ? 8 : 2));
 	if (const char* e = std::getenv("IPIC_STAGES")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) stages = v; }   // tuning knob
 }
 

@@ -15,6 +15,7 @@
 #include "particle_kernels.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace ipic {
 
@@ -54,6 +55,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 		"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
 		"selp.u32 %0, 1, 0, p;\n"
 		"}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+	return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// non-blocking probe of a phase
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+	uint32_t ok;
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+		"selp.u32 %0, 1, 0, p;\n"
+		"}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
 	return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -318,6 +333,214 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	}
 	if (PUSH && tid == 0) { countOut[cell] = kept; nLeave[cell] = left; }
 	if (DEPOSIT && tid < 24) cellJ[cellj_index(g, cx, cy, cz) + tid] = sJ[tid];      // GLOBAL cell id, z-major: a slab is contiguous
+}
+
+// ---- fused mover + deposit, warp-specialised ---------------------------------------------------------
+//
+// The analytic mover with the current deposit fused in (the headline configuration).  k_move<.., DEPOSIT> runs the
+// deposit and the push as two phases per batch of tiles in the same four warps: the 24 corner accumulators must be
+// dead while the mover's registers are live, the tiles are walked twice, and every batch pays a block reduction.
+// Here a FIFTH warp does the deposit: it walks every tile of the cell out of the same shared-memory stages the push
+// warps consume (one pass over HBM), keeps its 24 accumulators for the whole cell and reduces them once, with
+// shuffles, at the end.  It is also the TMA producer: a stage is re-armed once the push warps (named barrier + one
+// arrival) and the deposit warp (one arrival) are both done with it.  The FP64-heavy deposit stream and the
+// integer-heavy classify/compaction stream of the push warps interleave on the SM's schedulers.
+// The push warps' code is k_move's push phase unchanged, so particles, counts and tags are identical; the per-cell
+// corner sums are accumulated in a different (fixed) order: J stays within 1e-12 of the reference's.
+
+#ifndef IPIC_MINB_WS
+#define IPIC_MINB_WS 4           // B200 sweep (scripts/sweep_ws.sh): 5 CTAs/SM caps the kernel at 72 registers and the accumulators spill
+#endif
+
+template<int NF, bool MIGRATE>
+__global__ void __launch_bounds__(kBlock + 32, IPIC_MINB_WS)
+k_move_ws(const Geometry g, const ParticleArrays in, const ParticleArrays out, const int64_t* __restrict__ cellStart,
+          const int* __restrict__ countIn, int* __restrict__ countOut, int* __restrict__ nLeave,
+          unsigned char* __restrict__ tag, double* __restrict__ cellJ, const int* __restrict__ stopFlag, int zBegin, int zCount, int stages) {
+
+	constexpr int TILE = kBlock;
+	constexpr int TILE_DOUBLES = TILE * NF;
+	constexpr int BLOCK_DOUBLES = 32 * NF;
+
+	if (*stopFlag) return;
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int xy = blockIdx.x / zCount;
+	const int zl = zBegin + (blockIdx.x - xy * zCount);
+	const int cx = xy / g.ny, cy = xy - cx * g.ny, cz = g.z0 + zl;
+	const int cell = xy * g.lz + zl;
+
+	extern __shared__ __align__(128) double sTile[];             // stages x TILE_DOUBLES
+	__shared__ uint64_t sFull[kMaxStages], sEmpty[kMaxStages];
+	__shared__ int sCnt[2][kWarps];                              // per push warp: stayers | leavers << 16
+	__shared__ double sGeo[6];                                   // cell origin, cell centre
+
+	const int n = countIn[cell];
+	const int64_t base = cellStart[cell];
+	const int cap = (int)(cellStart[cell + 1] - base);
+	const double* __restrict__ src = in.d + base * NF;
+	double* __restrict__ dst = out.d + base * NF;
+	const int nTiles = (n + TILE - 1) / TILE;
+
+	if (tid >= 32 && tid < 35) {
+		const int a = tid - 32;
+		const int cc = a == 0 ? cx : (a == 1 ? cy : cz);
+		const double o = g.origin[a] + (double)cc * g.w[a];
+		sGeo[a] = o;
+		sGeo[3 + a] = o + g.hw[a];
+	}
+	if (tid == 0) {
+		for (int s = 0; s < stages; s++) { mbar_init(&sFull[s], 1); mbar_init(&sEmpty[s], 2); }
+	}
+	__syncthreads();
+	const double* org = sGeo;
+	const double* ctr = sGeo + 3;
+
+	if (warp == kWarps) {
+		// ================= deposit warp (and TMA producer) =================
+		auto issue = [&](int t, int s) {
+			const int first = t * TILE;
+			const int cnt = min(TILE, n - first);
+			const uint32_t bytes = (uint32_t)((cnt + 31) >> 5) * (BLOCK_DOUBLES * 8);
+			mbar_expect_tx(&sFull[s], bytes);
+			tma_bulk_g2s(sTile + s * TILE_DOUBLES, src + (int64_t)first * NF, bytes, &sFull[s]);
+		};
+		int nextIssue = min(stages, nTiles);                     // tiles [0, nextIssue) are on their way
+		if (lane == 0) for (int t = 0; t < nextIssue; t++) issue(t, t);
+		double acc[24];
+		#pragma unroll
+		for (int a = 0; a < 24; a++) acc[a] = 0.0;
+		int s = 0;
+		uint32_t phase = 0;
+		for (int t = 0; t < nTiles; t++) {
+			// re-arm the stages both sides are done with (tile T goes where tile T - stages was); block only for the tile needed now
+			if (lane == 0) {
+				while (nextIssue < nTiles && nextIssue - stages < t) {
+					const int ss = nextIssue % stages;
+					const uint32_t ph = (uint32_t)(nextIssue / stages - 1) & 1u;
+					if (nextIssue == t) mbar_wait(&sEmpty[ss], ph);
+					else if (!mbar_test(&sEmpty[ss], ph)) break;
+					issue(nextIssue, ss);
+					nextIssue++;
+				}
+			}
+			__syncwarp();
+			mbar_wait(&sFull[s], phase);
+			const double* tile = sTile + s * TILE_DOUBLES;
+			const int left = n - t * TILE;
+			#pragma unroll
+			for (int k = 0; k < kWarps; k++) {
+				if (k * 32 + lane < left) {
+					const double* p = tile + k * BLOCK_DOUBLES + lane;
+					// projectToDensityField (reference cell.h:810-816) weighs q*v with the trilinear basis (1-r | r) per axis.  The
+					// 8 corner weights span the monomials {1, x, y, z, xy, xz, yz, xyz} of the fractional position: accumulate
+					// the 8 x 3 monomial moments (37 FP64 operations per particle instead of 48) and expand once per cell.
+					const double rx = (p[0] - org[0]) * g.iw[0], ry = (p[32] - org[1]) * g.iw[1], rz = (p[64] - org[2]) * g.iw[2];
+					const double q = NF == 8 ? p[192] : g.uq;
+					const double jv[3] = { q * p[96], q * p[128], q * p[160] };
+					const double xy = rx * ry, xz = rx * rz, yz = ry * rz;
+					const double xyz = xy * rz;
+					#pragma unroll
+					for (int c = 0; c < 3; c++) {
+						acc[c] += jv[c];
+						acc[3 + c] = __fma_rn(jv[c], rx, acc[3 + c]);
+						acc[6 + c] = __fma_rn(jv[c], ry, acc[6 + c]);
+						acc[9 + c] = __fma_rn(jv[c], rz, acc[9 + c]);
+						acc[12 + c] = __fma_rn(jv[c], xy, acc[12 + c]);
+						acc[15 + c] = __fma_rn(jv[c], xz, acc[15 + c]);
+						acc[18 + c] = __fma_rn(jv[c], yz, acc[18 + c]);
+						acc[21 + c] = __fma_rn(jv[c], xyz, acc[21 + c]);
+					}
+				}
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&sEmpty[s]);
+			if (++s == stages) { s = 0; phase ^= 1; }
+		}
+		// the cell's 24 monomial moments: fixed-shape shuffle tree (every lane ends up with all of them) ...
+		#pragma unroll
+		for (int a = 0; a < 24; a++) {
+			double v = acc[a];
+			v += __shfl_xor_sync(0xffffffffu, v, 16);
+			v += __shfl_xor_sync(0xffffffffu, v, 8);
+			v += __shfl_xor_sync(0xffffffffu, v, 4);
+			v += __shfl_xor_sync(0xffffffffu, v, 2);
+			v += __shfl_xor_sync(0xffffffffu, v, 1);
+			acc[a] = v;
+		}
+		// ... expanded into the 8 corner sums, corner (a,b,c) = weight (a ? x : 1-x)(b ? y : 1-y)(c ? z : 1-z); lane = corner*3 + comp
+		double mine = 0.0;
+		#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			const double S1 = acc[c], Sx = acc[3 + c], Sy = acc[6 + c], Sz = acc[9 + c], Sxy = acc[12 + c], Sxz = acc[15 + c], Syz = acc[18 + c], Sxyz = acc[21 + c];
+			const double corner[8] = {
+				S1 - Sx - Sy - Sz + Sxy + Sxz + Syz - Sxyz,      // (0,0,0)
+				Sz - Sxz - Syz + Sxyz,                           // (0,0,1)
+				Sy - Sxy - Syz + Sxyz,                           // (0,1,0)
+				Syz - Sxyz,                                      // (0,1,1)
+				Sx - Sxy - Sxz + Sxyz,                           // (1,0,0)
+				Sxz - Sxyz,                                      // (1,0,1)
+				Sxy - Sxyz,                                      // (1,1,0)
+				Sxyz };                                          // (1,1,1)
+			#pragma unroll
+			for (int k = 0; k < 8; k++) if (lane == k * 3 + c) mine = corner[k];
+		}
+		if (lane < 24) cellJ[cellj_index(g, cx, cy, cz) + lane] = mine;      // GLOBAL cell id, z-major: a slab is contiguous
+		return;
+	}
+
+	// ================= push warps =================
+	const bool wallCell = cx == 0 || cy == 0 || cz == 0 || cx == g.nx - 1 || cy == g.ny - 1 || cz == g.nz - 1;
+	const bool fieldFree = g.magTemp == 0.0 && g.pic > 0.0 && g.dt > 0.0 && g.dt < 1e100;
+	const unsigned lt = (1u << lane) - 1u;
+	int kept = 0, left = 0, par = 0, s = 0;
+	uint32_t phase = 0;
+	for (int t = 0; t < nTiles; t++) {
+		const int idx = t * TILE + tid;
+		double px, py, pz, vx, vy, vz, pq, pm;
+		unsigned code = kTagNone;
+		mbar_wait(&sFull[s], phase);
+		if (idx < n) {
+			const double* p = sTile + s * TILE_DOUBLES + warp * BLOCK_DOUBLES + lane;
+			px = p[0]; py = p[32]; pz = p[64];
+			vx = p[96]; vy = p[128]; vz = p[160];
+			if (NF == 8) { pq = p[192]; pm = p[224]; } else { pq = g.uq; pm = g.uqom; }
+			if (!(fieldFree && field_free_push(g, px, py, pz, vx, vy, vz, pm))) {
+				Vec3 E, B;
+				dipole_field(g, px, py, pz, E, B);
+				push_with_fields(g, px, py, pz, vx, vy, vz, pm, E, B);
+			}
+			code = MIGRATE ? classify(g, wallCell, cx, cy, cz, ctr, px, py, pz, vx, vy, vz) : 13u;
+		}
+		const unsigned bs = __ballot_sync(0xffffffffu, code == 13u);
+		const unsigned bl = __ballot_sync(0xffffffffu, code < 27u && code != 13u);
+		if (lane == 0) sCnt[par][warp] = __popc(bs) | (__popc(bl) << 16);
+		asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");        // every push thread has its particle in registers
+		if (tid == 0) mbar_arrive(&sEmpty[s]);
+		int run = 0, mine = 0;
+		#pragma unroll
+		for (int w = 0; w < kWarps; w++) {
+			if (w == warp) mine = run;
+			run += sCnt[par][w];
+		}
+		const bool st = code == 13u, lv = code < 27u && code != 13u;
+		if (st || lv) {
+			int d;
+			if (st) d = kept + (mine & 0xffff) + __popc(bs & lt);
+			else {
+				d = cap - 1 - (left + (mine >> 16) + __popc(bl & lt));
+				tag[base + d] = (unsigned char)code;
+			}
+			double* q = dst + (int64_t)(d >> 5) * BLOCK_DOUBLES + (d & 31);
+			st_stream(q, px); st_stream(q + 32, py); st_stream(q + 64, pz);
+			st_stream(q + 96, vx); st_stream(q + 128, vy); st_stream(q + 160, vz);
+			if (NF == 8) { st_stream(q + 192, pq); st_stream(q + 224, pm); }
+		}
+		kept += run & 0xffff; left += run >> 16;
+		par ^= 1;
+		if (++s == stages) { s = 0; phase ^= 1; }
+	}
+	if (tid == 0) { countOut[cell] = kept; nLeave[cell] = left; }
 }
 
 // ---- chunked mover: several CTAs per cell ----------------------------------------------------------
@@ -1028,10 +1251,35 @@ static void launch_move_k(const MoveArgs& a, int grid, cudaStream_t st) {
 	                                                          a.fieldEB, a.cellJ, a.stopFlag, a.zBegin, a.zCount, stages);
 }
 
+template<int NF, bool MIGRATE>
+static void launch_move_ws(const MoveArgs& a, int grid, cudaStream_t st) {
+	static bool configured = false;
+	auto kernel = k_move_ws<NF, MIGRATE>;
+	if (!configured) {
+		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)move_smem_bytes(NF, kMaxStages));
+		configured = true;
+	}
+	const int stages = std::max(1, std::min(a.stages, kMaxStages));
+	kernel<<<grid, kBlock + 32, move_smem_bytes(NF, stages), st>>>(a.g, a.in, a.out, a.cellStart, a.countIn, a.countOut, a.nLeave, a.tag,
+	                                                               a.cellJ, a.stopFlag, a.zBegin, a.zCount, stages);
+}
+
+static bool use_warp_specialised() {
+	static int v = -1;
+	if (v < 0) { const char* e = std::getenv("IPIC_WS"); v = e ? (std::atoi(e) != 0) : 1; }
+	return v != 0;
+}
+
 template<int NF, bool INTERP, bool DEPOSIT>
 static void launch_move_t(const MoveArgs& a, cudaStream_t st) {
 	const int grid = a.g.nx * a.g.ny * a.zCount;
 	if (grid == 0) return;
+	// the deposit warp pays off when the push is light (field-free plasma: the push warps are integer / issue bound); with the
+	// analytic dipole every push carries a pow and ~150 FP64 operations, the four-warp kernel's 5 CTAs/SM of pushers win (B200: 0.61 vs 0.63 ms)
+	if (DEPOSIT && !INTERP && a.push && a.g.magTemp == 0.0 && use_warp_specialised()) {
+		if (a.migrate) launch_move_ws<NF, true>(a, grid, st); else launch_move_ws<NF, false>(a, grid, st);
+		return;
+	}
 	if (!a.push) { if (DEPOSIT) launch_move_k<NF, false, DEPOSIT, false, false>(a, grid, st); }
 	else if (a.migrate) launch_move_k<NF, INTERP, DEPOSIT, true, true>(a, grid, st);
 	else launch_move_k<NF, INTERP, DEPOSIT, false, true>(a, grid, st);
