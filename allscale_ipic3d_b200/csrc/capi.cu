@@ -244,11 +244,12 @@ void fillGeometry(ipic_ctx* c) {
 // are resident, so one particle per thread (72 / 96 registers, 7 / 5 CTAs per SM) wins over two, and few
 // stages win over many (shared memory caps the CTAs per SM): 2 stages = 16 KiB for the plain mover; with
 // the fused deposit a batch of 4 stages amortises the per-batch block reduction of the 24 corner sums.
-void pickTileShape(const ipic_ctx* c, bool deposit, int& stages) {
+void pickTileShape(const ipic_ctx* c, bool deposit, bool pushes, int& stages) {
 	const int64_t avg = c->meanPopulation;
 	const int64_t tile = 128;
 	// fused deposit, warp-specialised (k_move_ws): a deep ring decouples the deposit warp from the push warps (sweep: 8 > 6 > 4)
-	stages = (int)std::max<int64_t>(1, std::min<int64_t>((avg + avg / 8 + tile - 1) / tile, deposit ? 8 : 2));
+	const bool ws = deposit && pushes && c->g.magTemp == 0.0;      // launch_move's choice of k_move_ws
+	stages = (int)std::max<int64_t>(1, std::min<int64_t>((avg + avg / 8 + tile - 1) / tile, ws ? 8 : (deposit ? 4 : 2)));
 	if (const char* e = std::getenv("IPIC_STAGES")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) stages = v; }   // tuning knob
 }
 
@@ -688,7 +689,7 @@ MoveArgs moveArgs(ipic_ctx* c, const StepFlags& f, int zBegin, int zCount) {
 	ma.fieldEB = c->dEB; ma.cellJ = c->dCellJ; ma.stopFlag = c->dStop;
 	ma.zBegin = zBegin; ma.zCount = zCount;
 	ma.interpolate = f.interp; ma.migrate = f.migrate; ma.push = true; ma.deposit = f.fuseDeposit;
-	pickTileShape(c, ma.deposit, ma.stages);
+	pickTileShape(c, ma.deposit, !f.interp, ma.stages);
 	ma.chunked = false;
 	if (c->chunked) {
 		const int lz = c->g.lz;
@@ -717,7 +718,7 @@ void fieldPhase(ipic_ctx* c, const StepFlags& f) {
 void depositPass(ipic_ctx* c, const StepFlags& f, int zBegin, int zCount) {
 	MoveArgs da = moveArgs(c, f, zBegin, zCount);
 	da.push = false; da.deposit = true; da.interpolate = false;
-	pickTileShape(c, true, da.stages);
+	pickTileShape(c, true, false, da.stages);
 	launch_move(da, c->stream);
 	c->launches++;
 }

@@ -841,6 +841,7 @@ k_move_chunk(const Geometry g, const ParticleArrays in, const ParticleArrays out
 #endif
 constexpr int kImportBlock = IPIC_IMPORT_BLOCK;
 constexpr int kImportWarps = kImportBlock / 32;
+constexpr int kMedRounds = 4;              // the medium path of the import handles outboxes of up to 32 * kMedRounds entries
 
 // outbox entry j of a source: local outboxes grow backwards from the end of the cell's segment,
 // message columns forwards from the column's first entry
@@ -873,6 +874,7 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
          const int* __restrict__ stay, int* __restrict__ dstCount, int reserveOwnOutbox, int* __restrict__ stopFlag, int stepIndex, int zBegin, int zCount,
          const FaceMsg fromDown, const FaceMsg fromUp) {
 
+	__shared__ unsigned sMaskAll[kImportWarps][kMedRounds][27];      // medium path: match masks per (round, direction), one set per warp
 	if (*(volatile int*)stopFlag) return;
 	const int lane = threadIdx.x & 31;
 	const int task = blockIdx.x * kImportWarps + (threadIdx.x >> 5);
@@ -958,6 +960,60 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 				const int cnt = __popc(mask[d]);
 				if (i >= pre && i < pre + cnt) { dsel = d; jsel = (int)__fns(mask[d], 0, i - pre + 1); }
 				pre += cnt;
+			}
+			const int64_t base = __shfl_sync(0xffffffffu, myBase, dsel);
+			if (i < total && w + i < room) sourceOf(dsel).copyTo(base, jsel, dst.d + slot_index(dbase + w + i, g.nf));
+		}
+		w += total;
+	} else if (maxLeave <= 32 * kMedRounds) {
+		// medium flows (up to 128 leavers per neighbour: the dipole decks' ~90, the 8-GPU weak-scaling point's ~34): the
+		// same idea in rounds of 32 entries.  Pass 1 fetches, per round, all 26 tag rows at once and parks the 26 match
+		// masks in shared memory; lane d adds up its direction.  A scan over the lanes gives every direction its place in
+		// the canonical order; pass 2 copies 32 arrivals per trip, each lane finding its (direction, entry) from the masks.
+		unsigned (*sMask)[27] = sMaskAll[threadIdx.x >> 5];
+		const int rounds = (maxLeave + 31) >> 5;
+		int myCount = 0;
+		for (int r = 0; r < rounds; r++) {
+			unsigned char t[27];
+			#pragma unroll
+			for (int d = 0; d < 27; d++) {
+				if (d == 13) continue;
+				const int nl = __shfl_sync(0xffffffffu, myLeave, d);
+				const int64_t base = __shfl_sync(0xffffffffu, myBase, d);
+				const int j = r * 32 + lane;
+				t[d] = j < nl ? sourceOf(d).tagOf(base, j) : kTagNone;
+			}
+			#pragma unroll
+			for (int d = 0; d < 27; d++) {
+				if (d == 13) continue;
+				const unsigned want = (unsigned)((2 - d / 9) * 9 + (2 - (d / 3) % 3) * 3 + (2 - d % 3));
+				const unsigned m = __ballot_sync(0xffffffffu, t[d] == want);
+				if (lane == d) { sMask[r][d] = m; myCount += __popc(m); }
+			}
+		}
+		__syncwarp();
+		int incl = myCount;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+		const int dirBase = incl - myCount;                   // lane d: first arrival of direction d
+		const int total = __shfl_sync(0xffffffffu, incl, 31);
+		for (int i0 = 0; i0 < total; i0 += 32) {
+			const int i = i0 + lane;
+			int dsel = 0, rho = 0;
+			#pragma unroll
+			for (int d = 0; d < 27; d++) {
+				if (d == 13) continue;
+				const int b = __shfl_sync(0xffffffffu, dirBase, d), c = __shfl_sync(0xffffffffu, myCount, d);
+				if (i >= b && i < b + c) { dsel = d; rho = i - b; }
+			}
+			int jsel = 0;
+			if (i < total) {
+				for (int r = 0; r < rounds; r++) {
+					const unsigned m = sMask[r][dsel];
+					const int c = __popc(m);
+					if (rho < c) { jsel = r * 32 + (int)__fns(m, 0, rho + 1); break; }
+					rho -= c;
+				}
 			}
 			const int64_t base = __shfl_sync(0xffffffffu, myBase, dsel);
 			if (i < total && w + i < room) sourceOf(dsel).copyTo(base, jsel, dst.d + slot_index(dbase + w + i, g.nf));
