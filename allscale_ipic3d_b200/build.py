@@ -4,7 +4,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["capi.cu", "particle_kernels.cu", "field_kernels.cu", "diag_kernels.cu", "tracer_kernels.cu", "comm.cu"]
+SOURCES = ["capi.cu", "particle_kernels.cu", "field_kernels.cu", "diag_kernels.cu", "tracer_kernels.cu", "init_kernels.cu", "comm.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-fmad=false",            # no FMA contraction: bit-faithful FP64 vs the reference's x86-64 GCC build
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "-diag-suppress", "128"]

@@ -22,7 +22,7 @@ API_SYMBOLS = [
     "ipic_step_async", "ipic_sync", "ipic_count_misplaced", "ipic_profile_reset", "ipic_profile_get", "ipic_selftest",
     "ipic_set_exchange_capacity", "ipic_group_create", "ipic_group_step", "ipic_relayout_count",
     "ipic_alloc_pinned", "ipic_free_pinned", "ipic_set_uniform_species", "ipic_particle_fields", "ipic_profile_phases",
-    "ipic_diagnostics", "ipic_group_diagnostics", "ipic_trace",
+    "ipic_diagnostics", "ipic_group_diagnostics", "ipic_trace", "ipic_generate_uniform",
 ]
 
 
@@ -230,6 +230,10 @@ class Context:
         t = C.c_uint64(0)
         self._ck(self.lib.ipic_count_misplaced(self.h, C.byref(t)))
         return int(t.value)
+
+    def generate_uniform(self, num_particles):
+        """The reference's `:U:N` universe (this context's cells) generated on the device, bit-identical to initCells."""
+        self._ck(self.lib.ipic_generate_uniform(self.h, C.c_uint64(num_particles)))
 
     def diagnostics(self):
         """(total momentum, E energy, B energy, total kinetic energy): the columns of ConservedQuantities.out, reduced on the device."""

@@ -18,6 +18,7 @@
 #include "comm.h"
 #include "diag_kernels.h"
 #include "field_kernels.h"
+#include "init_kernels.h"
 #include "ipic_device.cuh"
 #include "particle_kernels.h"
 #include "tracer_kernels.h"
@@ -512,17 +513,63 @@ int ipic_particle_fields(ipic_ctx* c, int* fields) {
 	return IPIC_OK;
 }
 
+namespace {
+
+// Segment layout, storage and per-cell counters for the populations `need` (owned cells, slab order) in a layout of
+// nf fields per particle; the particles themselves are written afterwards (scatter of an upload, device generator).
+int establishLayout(ipic_ctx* c, const std::vector<int64_t>& need, int nf, double uq, double uqom) {
+	const int nOwned = ownedCells(c);
+	int64_t total = 0;
+	std::vector<int> localCount((size_t)c->g.ncellsLocal, 0);
+	for (int i = 0; i < nOwned; i++) { total += need[(size_t)i]; localCount[(size_t)i] = (int)need[(size_t)i]; }
+	c->g.nf = nf; c->g.uq = uq; c->g.uqom = uqom;
+	if (!c->userHeadroom) {
+		// sparse cells next to full ones fill up towards the mean (the dipole runs start with 12 particles per cell outside the
+		// inner box and ~1000 inside; diffusion levels that out): give every cell room for the mean population and a quarter,
+		// instead of paying a re-layout every few steps.  Evenly filled universes (:U:) keep the tight layout.
+		const int64_t mean = total / std::max(1, nOwned);
+		const int64_t least = need.empty() ? 0 : *std::min_element(need.begin(), need.end());
+		c->padFloor = least < mean / 4 ? mean + mean / 4 : 0;
+	}
+	std::vector<int64_t> start;
+	buildLayout(c, need, start);
+	if (start.back() > c->slots || start.back() < c->slots / 2 || c->slotsNf != nf) {
+		freeParticleBuffers(c);
+		int rc = allocParticleBuffers(c->buf, &c->dTag, start.back(), nf);
+		if (rc) return rc;
+		c->slots = start.back();
+		c->slotsNf = nf;
+	}
+	c->hCellStart = start;
+	int rc = buildChunkTable(c, need.empty() ? 0 : *std::max_element(need.begin(), need.end()));
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(c->dCellStart, start.data(), start.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->dCount, localCount.data(), localCount.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemsetAsync(c->dLeave, 0, (size_t)c->g.ncellsLocal * sizeof(int), c->stream));
+	CK(cudaStreamSynchronize(c->stream));     // the host vectors above go out of scope
+	c->haveCells = true;
+	c->emptyUpload = total == 0;
+	c->meanPopulation = total / std::max(1, nOwned);
+	if (c->nranks > 1) {
+		int64_t lo = 0, hi = 0;
+		for (int xy = 0; xy < c->g.nx * c->g.ny; xy++) { lo += need[(size_t)xy * c->g.lz]; hi += need[(size_t)xy * c->g.lz + c->g.lz - 1]; }
+		c->facePopulation = std::max(lo, hi);
+		c->exchangeDirty = true;
+	}
+	return IPIC_OK;
+}
+
+} // namespace
+
 int ipic_upload_cells(ipic_ctx* c, const uint64_t* counts, const double* aos) {
 	if (!c || !counts) return fail(IPIC_ERR_ARG, "null argument");
 	CK(cudaSetDevice(c->device));
 	const int nOwned = ownedCells(c);
 	std::vector<int64_t> need((size_t)nOwned), aosStart((size_t)nOwned + 1, 0);
-	std::vector<int> localCount((size_t)c->g.ncellsLocal, 0);
 	for (int i = 0; i < nOwned; i++) {
 		if (counts[i] > 0x3fffffffu) return fail(IPIC_ERR_ARG, "cell %d holds %llu particles (limit 2^30 per cell)", i, (unsigned long long)counts[i]);
 		need[i] = (int64_t)counts[i];
 		aosStart[i + 1] = aosStart[i] + need[i];
-		localCount[(size_t)i] = (int)counts[i];
 	}
 	const int64_t total = aosStart[nOwned];
 	if (total > 0 && !aos) return fail(IPIC_ERR_ARG, "particles_aos is null");
@@ -544,45 +591,35 @@ int ipic_upload_cells(ipic_ctx* c, const uint64_t* counts, const double* aos) {
 			if (!mixed) { nf = 6; uq = aos[6]; uqom = aos[7]; }
 		}
 	}
-	c->g.nf = nf; c->g.uq = uq; c->g.uqom = uqom;
-	if (!c->userHeadroom) {
-		// sparse cells next to full ones fill up towards the mean (the dipole runs start with 12 particles per cell outside the
-		// inner box and ~1000 inside; diffusion levels that out): give every cell room for the mean population and a quarter,
-		// instead of paying a re-layout every few steps.  Evenly filled universes (:U:) keep the tight layout.
-		const int64_t mean = total / std::max(1, nOwned);
-		const int64_t least = need.empty() ? 0 : *std::min_element(need.begin(), need.end());
-		c->padFloor = least < mean / 4 ? mean + mean / 4 : 0;
-	}
-	std::vector<int64_t> start;
-	buildLayout(c, need, start);
-	if (start.back() > c->slots || start.back() < c->slots / 2 || c->slotsNf != nf) {
-		freeParticleBuffers(c);
-		rc = allocParticleBuffers(c->buf, &c->dTag, start.back(), nf);
-		if (rc) return rc;
-		c->slots = start.back();
-		c->slotsNf = nf;
-	}
-	c->hCellStart = start;
-	rc = buildChunkTable(c, need.empty() ? 0 : *std::max_element(need.begin(), need.end()));
+	rc = establishLayout(c, need, nf, uq, uqom);
 	if (rc) return rc;
-	CK(cudaMemcpyAsync(c->dCellStart, start.data(), start.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
 	CK(cudaMemcpyAsync(c->dAosStart, aosStart.data(), aosStart.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-	CK(cudaMemcpyAsync(c->dCount, localCount.data(), localCount.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-	CK(cudaMemsetAsync(c->dLeave, 0, (size_t)c->g.ncellsLocal * sizeof(int), c->stream));
 	if (total) {
 		launch_scatter_aos(c->g, c->dStage, c->dAosStart, c->buf[c->cur], c->dCellStart, c->stream);
 		c->launches++;
 	}
-	CK(cudaStreamSynchronize(c->stream));     // host vectors above go out of scope
-	c->haveCells = true;
-	c->emptyUpload = total == 0;
-	c->meanPopulation = total / std::max(1, nOwned);
-	if (c->nranks > 1) {
-		int64_t lo = 0, hi = 0;
-		for (int xy = 0; xy < c->g.nx * c->g.ny; xy++) { lo += need[(size_t)xy * c->g.lz]; hi += need[(size_t)xy * c->g.lz + c->g.lz - 1]; }
-		c->facePopulation = std::max(lo, hi);
-		c->exchangeDirty = true;
+	CK(cudaStreamSynchronize(c->stream));     // aosStart goes out of scope
+	return IPIC_OK;
+}
+
+int ipic_generate_uniform(ipic_ctx* c, uint64_t numParticles) {
+	if (!c) return fail(IPIC_ERR_ARG, "null context");
+	CK(cudaSetDevice(c->device));
+	const Geometry& g = c->g;
+	const uint64_t numCells = (uint64_t)g.nx * g.ny * g.nz;
+	if (numParticles / numCells + 1 > 0x3fffffffu) return fail(IPIC_ERR_ARG, "%llu particles over %llu cells exceed 2^30 per cell", (unsigned long long)numParticles, (unsigned long long)numCells);
+	std::vector<int64_t> need((size_t)ownedCells(c));
+	for (int xy = 0; xy < g.nx * g.ny; xy++) for (int zl = 0; zl < g.lz; zl++) {
+		const uint64_t lin = (uint64_t)xy * g.nz + (uint64_t)(g.z0 + zl);      // the reference's flatten, z fastest (cell.h:521-523)
+		need[(size_t)xy * g.lz + zl] = (int64_t)(numParticles / numCells + (lin < numParticles % numCells ? 1 : 0));
 	}
+	const bool oneSpecies = c->allowUniformSpecies;
+	int rc = establishLayout(c, need, oneSpecies ? 6 : kFields, oneSpecies ? -1.0 : 0.0, oneSpecies ? -25.0 : 0.0);
+	if (rc) return rc;
+	launch_init_uniform(c->g, c->buf[c->cur], c->dCellStart, c->dCount, c->stream);
+	c->launches++;
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaGetLastError());
 	return IPIC_OK;
 }
 

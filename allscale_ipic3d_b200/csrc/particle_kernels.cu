@@ -841,7 +841,7 @@ k_move_chunk(const Geometry g, const ParticleArrays in, const ParticleArrays out
 #endif
 constexpr int kImportBlock = IPIC_IMPORT_BLOCK;
 constexpr int kImportWarps = kImportBlock / 32;
-constexpr int kMedRounds = 4;              // the medium path of the import handles outboxes of up to 32 * kMedRounds entries
+constexpr int kMedRounds = 16;             // the medium path of the import handles outboxes of up to 32 * kMedRounds entries
 
 // outbox entry j of a source: local outboxes grow backwards from the end of the cell's segment,
 // message columns forwards from the column's first entry
@@ -966,7 +966,7 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 		}
 		w += total;
 	} else if (maxLeave <= 32 * kMedRounds) {
-		// medium flows (up to 128 leavers per neighbour: the dipole decks' ~90, the 8-GPU weak-scaling point's ~34): the
+		// medium flows (up to 512 leavers per neighbour: the dipole decks' ~90, the 8-GPU weak-scaling point's ~34): the
 		// same idea in rounds of 32 entries.  Pass 1 fetches, per round, all 26 tag rows at once and parks the 26 match
 		// masks in shared memory; lane d adds up its direction.  A scan over the lanes gives every direction its place in
 		// the canonical order; pass 2 copies 32 arrivals per trip, each lane finding its (direction, entry) from the masks.

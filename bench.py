@@ -46,6 +46,9 @@ def parse_args():
                     help="uniform = the headline :U:N plasma; dipole = a secondary data point (fixed total, z-slabs over the ranks): the reference's Earth-dipole "
                          ".inp set-up (medium.inp physics: 0.625 R_E cells, 10 MeV protons, absorption, ~17 %% migration per step) on --grid^3 "
                          "cells with 8^3 particles per cell")
+    ap.add_argument("--device-init", action="store_true",
+                    help="device-resident leg only: create the :U: universe in HBM with ipic_generate_uniform (bit-identical to the host "
+                         "generator) instead of generating on the host and uploading; implies --no-e2e")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-particles", type=int, default=8_000_000, help="size of the bounded CPU sample")
@@ -214,6 +217,13 @@ def run_b200(args):
         n_local = int(counts.sum())
         host = torch.from_numpy(np.ascontiguousarray(aos)).pin_memory()
         del aos
+    elif args.device_init:
+        args.no_e2e = True
+        props = capi.uniform_benchmark_props(args.grid)
+        n_total = args.particles_per_gpu * world
+        counts = capi.uniform_counts(props, n_total, rank * lz, lz)
+        n_local = int(counts.sum())
+        host = None
     else:
         props = capi.uniform_benchmark_props(args.grid)
         n_total = args.particles_per_gpu * world
@@ -222,7 +232,7 @@ def run_b200(args):
         # the host universe of this slab, pinned (what simulateSteps hands to the C ABI)
         host = torch.empty((n_local, 8), dtype=torch.float64).pin_memory()
         capi.uniform_particles_into(props, n_total, host.data_ptr(), rank * lz, lz)
-    result = torch.empty((n_local + n_local // 8 + 4096, 8), dtype=torch.float64).pin_memory()
+    result = None if args.no_e2e else torch.empty((n_local + n_local // 8 + 4096, 8), dtype=torch.float64).pin_memory()
 
     flags = 0 if args.no_deposit else ipic.PROJECT_CURRENT
     ctx = ipic.Context(props, device=local, rank=rank, nranks=world)
@@ -230,7 +240,10 @@ def run_b200(args):
         uid = [ipic.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0])
-    ctx.upload_cells_ptr(counts, host.data_ptr())
+    if host is None:
+        ctx.generate_uniform(n_total)
+    else:
+        ctx.upload_cells_ptr(counts, host.data_ptr())
     particle_fields = ctx.particle_fields()
 
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps -------------------

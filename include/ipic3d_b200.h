@@ -124,6 +124,13 @@ IPIC_API int  ipic_group_step(ipic_ctx** ctxs, int n, uint64_t num_steps, uint32
  * (universe.h:12-27).  `counts` has one entry per cell of the GLOBAL grid when the context is the
  * whole universe, or of the slab (nx*ny*nz_local, same flatten) for slab contexts. */
 IPIC_API int  ipic_upload_cells(ipic_ctx* ctx, const uint64_t* counts, const double* particles_aos);
+/* The universe of the reference's `:U:N` benchmark created directly in HBM: initCells(properties, N, distribution::uniform<>)
+ * (cell.h:638-697) for the context's cells -- population N / cells (+1 for the first N % cells cells of the z-fastest
+ * flatten), per cell two std::minstd_rand engines seeded (x*1023 + y)*1023 + z + 1 / + 2, positions uniform in the cell's
+ * box and velocities uniform in [-0.2, 0.2]^3 through std::uniform_real_distribution<double> (libstdc++ generate_canonical:
+ * two engine calls per double), electrons (q -1, qom -25).  Bit-identical to the host generator: the LCG is jumped ahead
+ * per particle, the floating-point steps are the library's, unfused.  Replaces ipic_upload_cells for this universe. */
+IPIC_API int  ipic_generate_uniform(ipic_ctx* ctx, uint64_t num_particles);
 IPIC_API int  ipic_download_cells(ipic_ctx* ctx, uint64_t* counts, double* particles_aos, uint64_t capacity_particles);
 IPIC_API int  ipic_cell_counts(ipic_ctx* ctx, uint64_t* counts);
 IPIC_API int  ipic_total_particles(ipic_ctx* ctx, uint64_t* total);

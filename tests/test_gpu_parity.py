@@ -541,3 +541,33 @@ def test_diagnostics_uniform_benchmark():
     assert want[1] == 0.0 and want[2] == 0.0 and got[1] == 0.0 and got[2] == 0.0
     for i in (0, 3):
         assert abs(got[i] - want[i]) <= TOL * abs(want[i])
+
+
+@pytest.mark.parametrize("n", [1_000_003, 300_000])
+def test_device_generator_bit_identical(n):
+    """ipic_generate_uniform: the `:U:N` universe generated in HBM (LCG jump-ahead per particle, libstdc++'s
+    generate_canonical restated) is bit-identical to the reference's initCells, counts and every particle; also on 2 slabs
+    and in the 8-field layout."""
+    if not Ref.available():
+        pytest.skip("oracle/_ref not built")
+    r = Ref.uniform(n)
+    want_counts, want = r.counts(), r.particles()
+    with ctx_for(r.props) as c:
+        c.generate_uniform(n)
+        assert c.particle_fields() == 6
+        counts, aos = c.download_cells()
+        assert np.array_equal(counts, want_counts) and bits_equal(aos, want)
+        c.step(3); r.step(3)
+        counts, aos = c.download_cells()
+        assert np.array_equal(counts, r.counts()) and bits_equal(aos, r.particles())
+    with group_for(r.props, 2) as g:
+        for m in g.members:
+            m.generate_uniform(n)
+        counts, aos = g.download_cells()
+        assert np.array_equal(counts, want_counts) and bits_equal(aos, want)
+    with ctx_for(r.props) as c:
+        c.set_uniform_species(False)
+        c.generate_uniform(n)
+        assert c.particle_fields() == 8
+        counts, aos = c.download_cells()
+        assert np.array_equal(counts, want_counts) and bits_equal(aos, want)
