@@ -250,7 +250,8 @@ void pickTileShape(const ipic_ctx* c, bool deposit, bool pushes, int& stages) {
 	const int64_t tile = 128;
 	// fused deposit, warp-specialised (k_move_ws): a deep ring decouples the deposit warp from the push warps (sweep: 8 > 6 > 4)
 	const bool ws = deposit && pushes && c->g.magTemp == 0.0;      // launch_move's choice of k_move_ws
-	stages = (int)std::max<int64_t>(1, std::min<int64_t>((avg + avg / 8 + tile - 1) / tile, ws ? 8 : (deposit ? 4 : 2)));
+	// (8 stages of the 8-field layout are 64 KiB: six keep four CTAs per SM)
+	stages = (int)std::max<int64_t>(1, std::min<int64_t>((avg + avg / 8 + tile - 1) / tile, ws ? (c->g.nf == kFields ? 6 : 8) : (deposit ? 4 : 2)));
 	if (const char* e = std::getenv("IPIC_STAGES")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) stages = v; }   // tuning knob
 }
 
