@@ -268,7 +268,10 @@ def run_b200(args):
     mover_s = max_over_ranks(mover_ms / 1e3) / args.steps
     bpp = BYTES_PER_PUSH[particle_fields]
     achieved = n_local * bpp / mover_s / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_move (fused mover + deposit + classify/compaction)", "achieved": achieved,
+    kernel = ("k_move_ws (warp-specialised: 4 push warps + 1 deposit warp per cell; fused mover + deposit + classify/compaction)"
+              if (not args.no_deposit and args.workload == "uniform") else
+              "k_move (fused mover%s + classify/compaction)" % ("" if args.no_deposit else " + deposit"))
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "bytes_per_push": bpp, "pushes_per_launch": n_local, "launch_ms": mover_s * 1e3,
                 "at_survey_112B_per_push": {"achieved": n_local * SURVEY_BYTES_PER_PUSH / mover_s / 1e9,
