@@ -437,6 +437,19 @@ def uniform_universe(props, num_particles, z_begin=0, z_count=None, threads=0):
     return counts, aos
 
 
+def slab_of(counts, aos, nxy, nz, rank, world):
+    """The z-slab `rank` of `world` of a universe given as per-cell counts (z-fastest flatten) + cell-major AoS particles:
+    (counts, particles) of the slab's cells in slab order (x*ny + y)*lz + zl."""
+    counts = np.asarray(counts)
+    lz = nz // world
+    first = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    cells = (np.arange(nxy)[:, None] * nz + rank * lz + np.arange(lz)[None, :]).reshape(-1)
+    mine = counts[cells]
+    offset = np.concatenate([[0], np.cumsum(mine)[:-1]]).astype(np.int64)
+    idx = np.repeat(first[cells] - offset, mine.astype(np.int64)) + np.arange(int(mine.sum()))
+    return mine, np.asarray(aos).reshape(-1, 8)[idx]
+
+
 def dipole_universe(deck_path, grid, per_dim):
     """The reference's `ipic3d <deck>` universe (main()'s Earth set-up, two-phase initCells) built by the host C++ mirror,
     with the deck's grid replaced by grid^3 cells (box length scaled to keep the cell width) and per_dim^3 particles per cell."""

@@ -209,11 +209,7 @@ def run_b200(args):
         props, counts, aos = capi.dipole_universe(os.path.join(ROOT, "tests", "golden", "inputs", "medium.inp"), args.grid, 8)
         n_total = int(counts.sum())
         if world > 1:
-            first = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-            cells = (np.arange(nz * nz)[:, None] * nz + rank * lz + np.arange(lz)[None, :]).reshape(-1)    # slab order (x*ny + y)*lz + zl
-            counts = counts[cells]
-            idx = np.repeat(first[cells] - np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64), counts.astype(np.int64)) + np.arange(int(counts.sum()))
-            aos = aos[idx]
+            counts, aos = capi.slab_of(counts, aos, nz * nz, nz, rank, world)
         n_local = int(counts.sum())
         host = torch.from_numpy(np.ascontiguousarray(aos)).pin_memory()
         del aos
