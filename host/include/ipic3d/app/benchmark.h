@@ -1,9 +1,18 @@
-// Host C++ mirror: the synthetic benchmark driver `ipic3d :X:N` (reference hdr/benchmark.h:13-175):
-// 32^3 cells of width 10, dt 0.15, 2 warm-up + 5 timed steps, "Throughput: ... particles/s".
+// Host C++ mirror: the synthetic benchmark driver `ipic3d :X:N` (reference hdr/benchmark.h:13-175).
+//
+// The four loads are described once (`benchmarkUniverse`): a 32^3 grid of cells of width 10, dt 0.15 and a particle
+// generator per load; `processBenchmark` parses the `:X:N` designation, builds the universe, runs 2 warm-up and 5 timed
+// steps through simulateSteps (GPU) and prints the lines the reference's scripts grep ("Throughput: ... particles/s").
+//
+//   U  uniform    positions uniform over the universe, velocities uniform in [-0.2, 0.2]^3
+//   C  cluster    positions normal around the centre (sigma = size / 5), same velocities
+//   E  explosion  positions uniform in the central 20 % box clipped to a ball of radius size / 10, velocities normal (sigma 1.5)
+//   B  beam       positions normal around size / 100 (sigma size / 500), one velocity: 0.95 universe lengths in the timed steps
 #pragma once
 #include <chrono>
 #include <cstdlib>
 #include <iostream>
+#include <stdexcept>
 #include <string>
 
 #include "ipic3d/app/simulator.h"
@@ -19,82 +28,88 @@ namespace ipic3d {
 	const Vector3<double> CELL_WIDTH{ 10, 10, 10 };
 	const Vector3<double> UNIVERSE_SIZE{ GRID_SIZE.x * CELL_WIDTH.x, GRID_SIZE.y * CELL_WIDTH.y, GRID_SIZE.z * CELL_WIDTH.z };
 
-	inline int processUniverse(Universe& universe, std::uint64_t numParticles, std::uint64_t numTimeSteps, std::uint64_t numWarmupTimeSteps = NUM_WARMUP_TIME_STEPS) {
-		const bool dumpParticles = std::getenv("DUMP_PARTICLE_POSITION");
-		if (dumpParticles) outputParticlePositions(universe.cells, std::string("t_begin.txt"));
+	namespace detail {
+		inline UniverseProperties benchmarkProperties() {
+			UniverseProperties p;
+			p.size = GRID_SIZE;
+			p.cellWidth = CELL_WIDTH;
+			p.dt = DELTA_T;
+			p.FieldOutputCycle = 0;
+			return p;
+		}
+		inline InitProperties benchmarkInit() {
+			InitProperties init;
+			init.driftVelocity.push_back(0);
+			return init;
+		}
+	}
 
-		std::cout << "Running simulation on " << universe.properties.size << " grid ..." << std::endl;
-		std::cout << "Warming up for " << numWarmupTimeSteps << " timesteps ..." << std::endl;
+	// the universe of load `kind` with numParticles particles; numTimeSteps enters the beam's velocity (benchmark.h:126-138)
+	inline Universe benchmarkUniverse(char kind, std::uint64_t numParticles, std::uint64_t numTimeSteps = NUM_TIME_STEPS) {
+		const UniverseProperties props = detail::benchmarkProperties();
+		const InitProperties init = detail::benchmarkInit();
+		const Vector3<double> slow{ -0.2, -0.2, -0.2 }, fast{ +0.2, +0.2, +0.2 };
+		switch (kind) {
+			case 'U':
+				return createUniverseFromDistribution(props, init, numParticles, distribution::uniform<>(Vector3<double>{ 0, 0, 0 }, UNIVERSE_SIZE, slow, fast));
+			case 'C':
+				return createUniverseFromDistribution(props, init, numParticles, distribution::normal<>(UNIVERSE_SIZE / 2, UNIVERSE_SIZE / 5, slow, fast));
+			case 'E': {
+				using ball_fill = distribution::generic_particle_generator<distribution::vector::uniform, distribution::vector::normal, distribution::species::electron>;
+				const ball_fill inner({ UNIVERSE_SIZE * 0.4, UNIVERSE_SIZE * 0.6, 0 }, { Vector3<double>{ 0 }, Vector3<double>{ 1.5 }, 1 }, {});
+				return createUniverseFromDistribution(props, init, numParticles, distribution::make_spherical(inner, UNIVERSE_SIZE / 2, UNIVERSE_SIZE.x / 10));
+			}
+			case 'B': {
+				const Vector3<double> speed = UNIVERSE_SIZE / numTimeSteps * 0.95 / DELTA_T;
+				return createUniverseFromDistribution(props, init, numParticles, distribution::normal<>(UNIVERSE_SIZE / 100, UNIVERSE_SIZE / 500, speed, speed));
+			}
+			default:
+				throw std::invalid_argument("benchmark type must be one of U, C, E, B");
+		}
+	}
+
+	// warm-up + timed run of an existing universe; state persists across the two simulateSteps calls
+	inline int processUniverse(Universe& universe, std::uint64_t numParticles, std::uint64_t numTimeSteps, std::uint64_t numWarmupTimeSteps = NUM_WARMUP_TIME_STEPS) {
+		using clock = std::chrono::high_resolution_clock;
+		const bool dump = std::getenv("DUMP_PARTICLE_POSITION") != nullptr;
+		if (dump) outputParticlePositions(universe.cells, std::string("t_begin.txt"));
+
+		std::cout << "Running simulation on " << universe.properties.size << " grid ..." << std::endl
+		          << "Warming up for " << numWarmupTimeSteps << " timesteps ..." << std::endl;
 		simulateSteps(numWarmupTimeSteps, universe);
 
 		std::cout << "Starting benchmarking for " << numTimeSteps << " timesteps ..." << std::endl;
-		const auto start = std::chrono::high_resolution_clock::now();
+		const auto t0 = clock::now();
 		simulateSteps(numTimeSteps, universe);
-		const auto end = std::chrono::high_resolution_clock::now();
-		std::cout << "Benchmark simulation Finished" << std::endl;
+		const double seconds = std::chrono::duration_cast<std::chrono::milliseconds>(clock::now() - t0).count() / 1000.0;
+		std::cout << "Benchmark simulation Finished" << std::endl
+		          << "Benchmark took " << seconds << "s\n"
+		          << "Throughput: " << (numTimeSteps * numParticles) / seconds << " particles/s \n";
 
-		const double s = std::chrono::duration_cast<std::chrono::milliseconds>(end - start).count() / 1000.0;
-		std::cout << "Benchmark took " << s << "s\n";
-		std::cout << "Throughput: " << (numTimeSteps * numParticles) / s << " particles/s \n";
-
-		if (dumpParticles) outputParticlePositions(universe.cells, std::string("t_end.txt"));
+		if (dump) outputParticlePositions(universe.cells, std::string("t_end.txt"));
 		return EXIT_SUCCESS;
 	}
 
-	template<typename Distribution>
-	int processDistribution(const Distribution& dist, std::uint64_t numParticles, std::uint64_t numTimeSteps) {
-		UniverseProperties universeProperties;
-		universeProperties.cellWidth = CELL_WIDTH;
-		universeProperties.size = GRID_SIZE;
-		universeProperties.dt = DELTA_T;
-		universeProperties.FieldOutputCycle = 0;
-		InitProperties initProperties;
-		initProperties.driftVelocity.push_back(0);
+	inline int processLoad(char kind, std::uint64_t numParticles, std::uint64_t numTimeSteps) {
 		std::cout << "Creating Particles ..." << std::endl;
-		auto universe = createUniverseFromDistribution(universeProperties, initProperties, numParticles, dist);
+		Universe universe = benchmarkUniverse(kind, numParticles, numTimeSteps);
 		return processUniverse(universe, numParticles, numTimeSteps);
 	}
+	inline int processUniform(std::uint64_t numParticles, std::uint64_t numTimeSteps) { return processLoad('U', numParticles, numTimeSteps); }
+	inline int processCluster(std::uint64_t numParticles, std::uint64_t numTimeSteps) { return processLoad('C', numParticles, numTimeSteps); }
+	inline int processExplosion(std::uint64_t numParticles, std::uint64_t numTimeSteps) { return processLoad('E', numParticles, numTimeSteps); }
+	inline int processBeam(std::uint64_t numParticles, std::uint64_t numTimeSteps) { return processLoad('B', numParticles, numTimeSteps); }
 
-	inline int processUniform(std::uint64_t numParticles, std::uint64_t numTimeSteps) {
-		return processDistribution(distribution::uniform<>(Vector3<double>{ 0, 0, 0 }, UNIVERSE_SIZE, Vector3<double>{ -0.2, -0.2, -0.2 }, Vector3<double>{ +0.2, +0.2, +0.2 }),
-		                           numParticles, numTimeSteps);
-	}
-
-	inline int processCluster(std::uint64_t numParticles, std::uint64_t numTimeSteps) {
-		return processDistribution(distribution::normal<>(UNIVERSE_SIZE / 2, UNIVERSE_SIZE / 5, Vector3<double>{ -0.2, -0.2, -0.2 }, Vector3<double>{ +0.2, +0.2, +0.2 }),
-		                           numParticles, numTimeSteps);
-	}
-
-	inline int processExplosion(std::uint64_t numParticles, std::uint64_t numTimeSteps) {
-		using generator = distribution::generic_particle_generator<distribution::vector::uniform, distribution::vector::normal, distribution::species::electron>;
-		return processDistribution(distribution::make_spherical(generator({ UNIVERSE_SIZE * 0.4, UNIVERSE_SIZE * 0.6, 0 }, { Vector3<double>{ 0 }, Vector3<double>{ 1.5 }, 1 }, {}),
-		                                                        UNIVERSE_SIZE / 2, UNIVERSE_SIZE.x / 10),
-		                           numParticles, numTimeSteps);
-	}
-
-	inline int processBeam(std::uint64_t numParticles, std::uint64_t numTimeSteps) {
-		return processDistribution(distribution::normal<>(UNIVERSE_SIZE / 100, UNIVERSE_SIZE / 500, UNIVERSE_SIZE / numTimeSteps * 0.95 / DELTA_T,
-		                                                  UNIVERSE_SIZE / numTimeSteps * 0.95 / DELTA_T),
-		                           numParticles, numTimeSteps);
-	}
-
+	// ":X:N" -> run load X with N particles; anything else prints the usage and fails
 	inline int processBenchmark(const std::string& config) {
 		std::cout << "Processing benchmark " << config << "\n";
-		auto showHelp = []() {
+		const bool wellFormed = config.length() > 3 && config[0] == ':' && config[2] == ':' && std::string("UCEB").find(config[1]) != std::string::npos;
+		if (!wellFormed) {
 			std::cout << "Benchmark designation: :X:N\n      X ... benchmark type:\n           U ... uniform\n           C ... cluster\n"
 			          << "           E ... explosion\n           B ... beam\n      N ... total number of particles\n";
 			return EXIT_FAILURE;
-		};
-		if (config.length() <= 3 || config[0] != ':' || config[2] != ':') return showHelp();
-		const std::uint64_t numTimeSteps = NUM_TIME_STEPS;
-		const std::uint64_t numParticles = (std::uint64_t)std::atoll(config.substr(3).c_str());
-		switch (config[1]) {
-			case 'U': return processUniform(numParticles, numTimeSteps);
-			case 'C': return processCluster(numParticles, numTimeSteps);
-			case 'E': return processExplosion(numParticles, numTimeSteps);
-			case 'B': return processBeam(numParticles, numTimeSteps);
-			default:  return showHelp();
 		}
+		return processLoad(config[1], (std::uint64_t)std::atoll(config.substr(3).c_str()), NUM_TIME_STEPS);
 	}
 
 } // namespace ipic3d

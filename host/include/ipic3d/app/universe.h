@@ -13,43 +13,52 @@ namespace ipic3d {
 
 	struct Universe {
 		const UniverseProperties properties;
-		Cells cells;
-		Field field;
-		BcField bcfield;
-		CurrentDensity currentDensity;
+		Cells cells;                       // size^3
+		Field field;                       // (size + 3)^3: nodes with one ghost layer
+		BcField bcfield;                   // (size + 2)^3: cell centres with ghost layer
+		CurrentDensity currentDensity;     // (size + 1)^3: nodes
 
+		// an empty universe of the given shape
 		explicit Universe(const UniverseProperties& properties = UniverseProperties())
-			: properties(properties), cells(properties.size), field(properties.size + coordinate_type(3)),
-			  bcfield(properties.size + coordinate_type(2)), currentDensity(properties.size + coordinate_type(1)) {}
+			: Universe(properties, Cells(properties.size), Field(properties.size + coordinate_type(3)),
+			           BcField(properties.size + coordinate_type(2)), CurrentDensity(properties.size + coordinate_type(1))) {}
 
+		// takes ownership of grids built elsewhere; their shapes must fit the properties
 		Universe(const UniverseProperties& properties, Cells&& cs, Field&& f, BcField&& bcf, CurrentDensity&& cD)
 			: properties(properties), cells(std::move(cs)), field(std::move(f)), bcfield(std::move(bcf)), currentDensity(std::move(cD)) {
-			assert(cells.size() == properties.size);
-			assert(field.size() == properties.size + coordinate_type(3));
-			assert(bcfield.size() == properties.size + coordinate_type(2));
-			assert(currentDensity.size() == properties.size + coordinate_type(1));
+			assert(shapesFit());
+		}
+
+		bool shapesFit() const {
+			const coordinate_type& n = properties.size;
+			return cells.size() == n && field.size() == n + coordinate_type(3) && bcfield.size() == n + coordinate_type(2) &&
+			       currentDensity.size() == n + coordinate_type(1);
 		}
 	};
 
-	inline Universe createUniverseFromParams(const Parameters& params, const std::string& baseName) {
-		const InitProperties initProperties(params);
-		std::cout << initProperties;
-		UniverseProperties universeProperties(params);
-		universeProperties.outputFileBaseName = baseName;
-		std::cout << universeProperties;
-		Cells cells = initCells(params, initProperties, universeProperties);
-		Field field = initFields(initProperties, universeProperties);
-		BcField bcField = initBcFields(universeProperties, field);
-		return Universe(universeProperties, std::move(cells), std::move(field), std::move(bcField), initCurrentDensity(universeProperties));
+	namespace detail {
+		// the grids every factory adds to a set of cells: dipole field on the nodes, its cell-centred average, J = 0
+		inline Universe assembleUniverse(const UniverseProperties& properties, const InitProperties& initProperties, Cells&& cells) {
+			Field field = initFields(initProperties, properties);
+			BcField bcField = initBcFields(properties, field);
+			return Universe(properties, std::move(cells), std::move(field), std::move(bcField), initCurrentDensity(properties));
+		}
 	}
 
+	// `ipic3d <deck>` as the decks describe it (maxwellian per cell; reference universe.h:56-80)
+	inline Universe createUniverseFromParams(const Parameters& params, const std::string& baseName) {
+		const InitProperties initProperties(params);
+		UniverseProperties universeProperties(params);
+		universeProperties.outputFileBaseName = baseName;
+		std::cout << initProperties << universeProperties;
+		return detail::assembleUniverse(universeProperties, initProperties, initCells(params, initProperties, universeProperties));
+	}
+
+	// numParticles particles drawn from a generator and sorted into cells (reference universe.h:85-105)
 	template<typename Distribution>
 	Universe createUniverseFromDistribution(const UniverseProperties& universeProperties, const InitProperties& initProperties,
 	                                        std::uint64_t numParticles, const Distribution& distribution) {
-		Cells cells = initCells(universeProperties, numParticles, distribution);
-		Field field = initFields(initProperties, universeProperties);
-		BcField bcField = initBcFields(universeProperties, field);
-		return Universe(universeProperties, std::move(cells), std::move(field), std::move(bcField), initCurrentDensity(universeProperties));
+		return detail::assembleUniverse(universeProperties, initProperties, initCells(universeProperties, numParticles, distribution));
 	}
 
 	inline std::uint64_t countParticlesInDomain(const Universe& universe) { return countParticlesInDomain(universe.cells); }

@@ -14,42 +14,58 @@ namespace ipic3d {
 	inline std::ostream& operator<<(std::ostream& out, const UseCase& useCase) { return out << (useCase == UseCase::Dipole ? "Dipole" : "Test"); }
 
 	struct UniverseProperties {
-		UseCase useCase;
-		coordinate_type size;                          // cells per dimension (cubic universes only, as in the reference)
-		Vector3<double> cellWidth;
-		double dt;
-		double speedOfLight;
-		double planetRadius;
-		Vector3<double> objectCenter;
-		Vector3<double> origin;                        // front lower left corner of the domain
-		Vector3<double> externalMagneticField;
-		int FieldOutputCycle;
-		int ParticleOutputCycle;
+		UseCase useCase = UseCase::Dipole;
+		coordinate_type size{ 1, 1, 1 };               // cells per dimension (cubic universes only, as in the reference)
+		Vector3<double> cellWidth{ 1.0, 1.0, 1.0 };
+		double dt = 1.0;
+		double speedOfLight = 1.0;
+		double planetRadius = 0.0;
+		Vector3<double> objectCenter{ 0.0, 0.0, 0.0 };
+		Vector3<double> origin{ 0.0, 0.0, 0.0 };       // front lower left corner of the domain
+		Vector3<double> externalMagneticField{ 0, 0, 0 };
+		int FieldOutputCycle = 100;
+		int ParticleOutputCycle = 100;
 		std::string outputFileBaseName;
 
-		UniverseProperties(const UseCase& useCase = UseCase::Dipole, const coordinate_type& size = { 1, 1, 1 },
-		                   const Vector3<double>& cellWidth = { 1.0, 1.0, 1.0 }, double dt = 1.0, double speedOfLight = 1.0,
-		                   double planetRadius = 0.0, const Vector3<double>& objectCenter = { 0.0, 0.0, 0.0 },
+		UniverseProperties() = default;
+
+		UniverseProperties(const UseCase& useCase, const coordinate_type& size = { 1, 1, 1 }, const Vector3<double>& cellWidth = { 1.0, 1.0, 1.0 },
+		                   double dt = 1.0, double speedOfLight = 1.0, double planetRadius = 0.0, const Vector3<double>& objectCenter = { 0.0, 0.0, 0.0 },
 		                   const Vector3<double>& origin = { 0.0, 0.0, 0.0 }, const Vector3<double>& externalMagneticField = { 0, 0, 0 },
-		                   int FieldOutputCycle = 100, int ParticleOutputCycle = 100)
-			: useCase(useCase), size(size), cellWidth(cellWidth), dt(dt), speedOfLight(speedOfLight), planetRadius(planetRadius),
-			  objectCenter(objectCenter), origin(origin), externalMagneticField(externalMagneticField),
-			  FieldOutputCycle(FieldOutputCycle), ParticleOutputCycle(ParticleOutputCycle) {
+		                   int FieldOutputCycle = 100, int ParticleOutputCycle = 100) {
+			this->useCase = useCase; this->size = size; this->cellWidth = cellWidth;
+			this->dt = dt; this->speedOfLight = speedOfLight; this->planetRadius = planetRadius;
+			this->objectCenter = objectCenter; this->origin = origin; this->externalMagneticField = externalMagneticField;
+			this->FieldOutputCycle = FieldOutputCycle; this->ParticleOutputCycle = ParticleOutputCycle;
+			validate();
+		}
+
+		// from an input deck: the box is centred on the object (reference universe_properties.h:92-113)
+		explicit UniverseProperties(const Parameters& params) {
+			useCase = params.useCase;
+			dt = params.dt;
+			speedOfLight = params.c;
+			planetRadius = params.planetRadius;
+			FieldOutputCycle = params.FieldOutputCycle;
+			ParticleOutputCycle = params.ParticlesOutputCycle;
+			const double centre[3] = { params.objectCenter.x, params.objectCenter.y, params.objectCenter.z };
+			const std::int64_t cells[3] = { params.ncells.x, params.ncells.y, params.ncells.z };
+			const double width[3] = { params.dspace.x, params.dspace.y, params.dspace.z };
+			const double field[3] = { params.B1.x, params.B1.y, params.B1.z };
+			for (int a = 0; a < 3; ++a) {
+				size[a] = cells[a];
+				cellWidth[a] = width[a];
+				objectCenter[a] = centre[a];
+				origin[a] = centre[a] - cells[a] * width[a] / 2.0;
+				externalMagneticField[a] = field[a];
+			}
+		}
+
+		void validate() const {
 			assert(size.x > 0 && size.y > 0 && size.z > 0);
 			assert(size.x == size.y && size.y == size.z);
 			assert(cellWidth.x > 0 && cellWidth.y > 0 && cellWidth.z > 0);
 			assert(dt > 0 && speedOfLight > 0 && planetRadius >= 0);
-		}
-
-		explicit UniverseProperties(const Parameters& params)
-			: useCase(params.useCase), size({ params.ncells.x, params.ncells.y, params.ncells.z }),
-			  cellWidth({ params.dspace.x, params.dspace.y, params.dspace.z }), dt(params.dt), speedOfLight(params.c),
-			  planetRadius(params.planetRadius), objectCenter({ params.objectCenter.x, params.objectCenter.y, params.objectCenter.z }),
-			  FieldOutputCycle(params.FieldOutputCycle), ParticleOutputCycle(params.ParticlesOutputCycle) {
-			origin.x = params.objectCenter.x - params.ncells.x * params.dspace.x / 2.0;
-			origin.y = params.objectCenter.y - params.ncells.y * params.dspace.y / 2.0;
-			origin.z = params.objectCenter.z - params.ncells.z * params.dspace.z / 2.0;
-			externalMagneticField = { params.B1.x, params.B1.y, params.B1.z };
 		}
 
 		// the POD mirror that crosses the C ABI
@@ -62,15 +78,25 @@ namespace ipic3d {
 			p.dt = dt; p.speedOfLight = speedOfLight; p.planetRadius = planetRadius;
 			return p;
 		}
-
-		friend std::ostream& operator<<(std::ostream& out, const UniverseProperties& p) {
-			return out << "Universe properties:\n\tUse Case: " << p.useCase << "\n\tSize: " << p.size << "\n\tCell width: " << p.cellWidth
-			           << "\n\tTimestep: " << p.dt << "\n\tSpeed of light: " << p.speedOfLight << "\n\tPlanet radius: " << p.planetRadius
-			           << "\n\tObject center: " << p.objectCenter << "\n\tOrigin of the domain: " << p.origin
-			           << "\n\tExternal magnetic field: " << p.externalMagneticField << "\n\tFields output cycle: " << p.FieldOutputCycle
-			           << "\n\tParticles output cycle: " << p.ParticleOutputCycle << std::endl;
-		}
 	};
+
+	// the console block the drivers print (one "\t<label>: <value>" line per property)
+	inline std::ostream& operator<<(std::ostream& out, const UniverseProperties& p) {
+		out << "Universe properties:\n";
+		auto line = [&out](const char* label, const auto& value) { out << "\t" << label << ": " << value << "\n"; };
+		line("Use Case", p.useCase);
+		line("Size", p.size);
+		line("Cell width", p.cellWidth);
+		line("Timestep", p.dt);
+		line("Speed of light", p.speedOfLight);
+		line("Planet radius", p.planetRadius);
+		line("Object center", p.objectCenter);
+		line("Origin of the domain", p.origin);
+		line("External magnetic field", p.externalMagneticField);
+		line("Fields output cycle", p.FieldOutputCycle);
+		line("Particles output cycle", p.ParticleOutputCycle);
+		return out << std::flush;
+	}
 
 	// origin + idx * width: position of the lower corner of a cell; the same formula locates field nodes
 	inline Vector3<double> getOriginOfCell(const coordinate_type& pos, const UniverseProperties& properties) {

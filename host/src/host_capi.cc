@@ -88,6 +88,7 @@ IPIC_API int ipic_host_uniform_particles(const ipic_props* p, uint64_t numPartic
 #include <sstream>
 
 #include "ipic3d/app/benchmark.h"
+#include "ipic3d/app/earth_deck.h"
 #include "ipic3d/app/universe.h"
 
 namespace {
@@ -98,31 +99,12 @@ struct MirrorUniverse {
 	explicit MirrorUniverse(ipic3d::Universe&& u) : universe(std::move(u)) {}
 };
 
-// main()'s set-up for "<file>.inp" (host/src/ipic3d.cc), without running anything
+// main()'s set-up for "<file>.inp" (EarthDeck, shared with host/src/ipic3d.cc), without running anything
 MirrorUniverse* mirrorFromInp(const char* path) {
-	using namespace ipic3d;
-	const Parameters params{ std::string(path) };
-	const InitProperties initProperties(params);
-	UniverseProperties up(params);
-	up.dt = 0.01;
-	up.speedOfLight = 299792458;
-	up.planetRadius = 6378137;
-	up.cellWidth *= up.planetRadius;
-	const auto universeSize = elementwiseProduct(up.cellWidth, up.size);
-	up.objectCenter = { 0.0, 0.0, 0.0 };
-	up.origin = up.objectCenter - universeSize / 2.0;
-	up.externalMagneticField = { 0.0, 0.0, 3.07e-5 };
-	up.useCase = UseCase::Dipole;
-	int numParticles = (int)(up.size.x * up.size.y * up.size.z);
-	numParticles = numParticles * initProperties.particlesPerCell[0].x * initProperties.particlesPerCell[0].y * initProperties.particlesPerCell[0].z;
-	const double e = 1.602176565e-19, K = 1e7 * e, m = 1.672621777e-27;
-	const double v_mod = up.speedOfLight / std::sqrt(1.0 + (m * up.speedOfLight * up.speedOfLight) / K);
-	const auto low = up.origin + 0.125 * universeSize;
-	const auto hig = low + 0.75 * universeSize;
-	const auto dist = distribution::uniform_pos_normal_speed<>(low, hig, Vector3<double>{ 0, 0, 0 }, Vector3<double>{ v_mod, v_mod, v_mod });
-	auto* h = new MirrorUniverse(createUniverseFromDistribution(up, initProperties, numParticles, dist));
-	h->ncycles = params.ncycles;
-	h->numParticles = (std::uint64_t)numParticles;
+	const ipic3d::EarthDeck deck{ std::string(path) };
+	auto* h = new MirrorUniverse(deck.createUniverse());
+	h->ncycles = deck.params.ncycles;
+	h->numParticles = (std::uint64_t)deck.numParticles;
 	return h;
 }
 
@@ -141,29 +123,15 @@ IPIC_API void* ipic_mirror_create_from_inp(const char* path, ipic_props* props, 
 	return h;
 }
 
-// benchmark.h processDistribution's universe for `:U:N` (kind 'U'), `:C:N` ('C'), `:E:N` ('E'), `:B:N` ('B')
+// benchmark.h's universe for `:U:N` (kind 'U'), `:C:N` ('C'), `:E:N` ('E'), `:B:N` ('B')
 IPIC_API void* ipic_mirror_create_benchmark(char kind, uint64_t numParticles, ipic_props* props) {
-	using namespace ipic3d;
+	if (std::string("UCEB").find(kind) == std::string::npos) return nullptr;
 	std::ostringstream quiet;
 	auto* old = std::cout.rdbuf(quiet.rdbuf());
-	UniverseProperties up;
-	up.cellWidth = CELL_WIDTH; up.size = GRID_SIZE; up.dt = DELTA_T; up.FieldOutputCycle = 0;
-	InitProperties ip;
-	ip.driftVelocity.push_back(0);
-	MirrorUniverse* h = nullptr;
-	const Vector3<double> vlo{ -0.2, -0.2, -0.2 }, vhi{ +0.2, +0.2, +0.2 };
-	if (kind == 'U') h = new MirrorUniverse(createUniverseFromDistribution(up, ip, numParticles, distribution::uniform<>(Vector3<double>{ 0, 0, 0 }, UNIVERSE_SIZE, vlo, vhi)));
-	else if (kind == 'C') h = new MirrorUniverse(createUniverseFromDistribution(up, ip, numParticles, distribution::normal<>(UNIVERSE_SIZE / 2, UNIVERSE_SIZE / 5, vlo, vhi)));
-	else if (kind == 'B') h = new MirrorUniverse(createUniverseFromDistribution(up, ip, numParticles,
-		distribution::normal<>(UNIVERSE_SIZE / 100, UNIVERSE_SIZE / 500, UNIVERSE_SIZE / NUM_TIME_STEPS * 0.95 / DELTA_T, UNIVERSE_SIZE / NUM_TIME_STEPS * 0.95 / DELTA_T)));
-	else if (kind == 'E') {
-		using generator = distribution::generic_particle_generator<distribution::vector::uniform, distribution::vector::normal, distribution::species::electron>;
-		h = new MirrorUniverse(createUniverseFromDistribution(up, ip, numParticles,
-			distribution::make_spherical(generator({ UNIVERSE_SIZE * 0.4, UNIVERSE_SIZE * 0.6, 0 }, { Vector3<double>{ 0 }, Vector3<double>{ 1.5 }, 1 }, {}), UNIVERSE_SIZE / 2, UNIVERSE_SIZE.x / 10)));
-	}
+	MirrorUniverse* h = new MirrorUniverse(ipic3d::benchmarkUniverse(kind, numParticles));
 	std::cout.rdbuf(old);
-	if (h && props) *props = h->universe.properties.toAbi();
-	if (h) h->numParticles = numParticles;
+	if (props) *props = h->universe.properties.toAbi();
+	h->numParticles = numParticles;
 	return h;
 }
 
