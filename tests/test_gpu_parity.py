@@ -571,3 +571,26 @@ def test_device_generator_bit_identical(n):
         assert c.particle_fields() == 8
         counts, aos = c.download_cells()
         assert np.array_equal(counts, want_counts) and bits_equal(aos, want)
+
+
+@pytest.mark.parametrize("one_species", [True, False])
+def test_fused_deposit_deep_cells(one_species):
+    """The warp-specialised mover + deposit (k_move_ws) on cells of ~2500 particles = 20 tiles, i.e. well past the 8-stage
+    ring (stages re-armed by the deposit warp while the push warps run), in both particle layouts: J within 1e-12 of
+    max|J| of the reference's projectToDensityField, particles and counts bit-exact, 3 steps."""
+    if not Ref.available():
+        pytest.skip("oracle/_ref not built")
+    props = Props.make(2, cellWidth=(10.0, 10.0, 10.0), dt=0.15 * 20)
+    r = Ref.uniform_grid(props, 20000)
+    flags = harness.PROJECT_CURRENT
+    with ctx_for(props) as c:
+        c.set_uniform_species(one_species)
+        c.upload_cells(r.counts(), r.particles())
+        assert c.particle_fields() == (6 if one_species else 8)
+        for step in range(3):
+            c.step(1, flags); r.step(1, flags)
+            _, _, j = c.download_fields()
+            want = r.density()
+            assert np.max(np.abs(j - want)) <= TOL * np.max(np.abs(want)), step
+        counts, aos = c.download_cells()
+    assert np.array_equal(counts, r.counts()) and bits_equal(aos, r.particles())
