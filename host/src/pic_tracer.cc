@@ -7,7 +7,7 @@
 // The reference hands `map(a, b)` sub-ranges of [0, N/B+1) to its runtime and seeds each task's generator with a*b,
 // so WHICH particles it traces depends on how the runtime splits the range.  This driver follows the sequential
 // schedule (one task covering the whole range: seed 0, particles 0..N-1), which is what the reference does when
-// built against a sequential preduce (oracle/shim).
+// built against a sequential preduce.
 #include <algorithm>
 #include <chrono>
 #include <cinttypes>

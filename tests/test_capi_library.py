@@ -55,3 +55,22 @@ def test_no_cuda_device_fails_loudly():
     with pytest.raises(ipic.IpicError) as e:
         ipic.Context(ipic.Props.make(4))
     assert e.value.code == -2
+    # the context-free entry points as well: the tracer and the device self-test have no CPU path either
+    import numpy as np
+    from allscale_ipic3d_b200 import capi
+    with pytest.raises(ipic.IpicError) as e:
+        capi.trace(ipic.Props.make(4, planetRadius=0.1), np.ones((3, 8)), 5, 1)
+    assert e.value.code == -2
+    with pytest.raises(ipic.IpicError):
+        capi.selftest(1 << 10)
+
+
+def test_host_tree_never_touches_the_oracle():
+    """Neither do the host C++ mirror and its drivers."""
+    for sub in ("host", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith((".h", ".cc", ".cpp", ".hpp")):
+                    text = open(os.path.join(dirpath, f), errors="ignore").read()
+                    assert "oracle" not in text.lower(), \
+                        "%s refers to the oracle tree" % os.path.join(dirpath, f)
