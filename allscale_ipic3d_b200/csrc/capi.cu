@@ -100,6 +100,10 @@ struct ipic_ctx {
 	double phaseMs[4] = { 0, 0, 0, 0 };             // slab steps: [0] movers (span), [1] imports, [2] waiting for the exchange, [3] waiting for J + field phase
 	uint64_t launches = 0;
 	uint64_t relayouts = 0;                        // cell-segment overflows repaired so far
+	// batch enqueued by ipic_step_async and not yet settled: generation at its start, steps, flags
+	uint64_t asyncSteps = 0;
+	int asyncGenAtStart = 0;
+	uint32_t asyncFlags = 0;
 
 	// z-slab exchange (nranks > 1): NCCL communicator (one process per GPU) or an in-process group
 	ipic_comm* comm = nullptr;
@@ -321,10 +325,13 @@ int relayoutAfterOverflow(ipic_ctx* c, int outGen, int failedStep) {
 	}
 	buildLayout(c, need64, newStart);
 	ParticleArrays nb[2]{}; unsigned char* ntag = nullptr;
+	int64_t* dNewStart = nullptr;
+	// until the new storage is swapped in, a failure frees it again
+	struct Fresh { ParticleArrays* nb; unsigned char** tag; int64_t** start; bool armed;
+	               ~Fresh() { if (armed) { cudaFree(nb[0].d); cudaFree(nb[1].d); cudaFree(*tag); cudaFree(*start); } } } fresh{ nb, &ntag, &dNewStart, true };
 	const int64_t nslots = newStart.back();
 	rc = allocParticleBuffers(nb, &ntag, nslots, c->g.nf);
 	if (rc) return rc;
-	int64_t* dNewStart = nullptr;
 	CK(cudaMalloc(&dNewStart, newStart.size() * sizeof(int64_t)));
 	CK(cudaMemcpyAsync(dNewStart, newStart.data(), newStart.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
 	CK(cudaMemsetAsync(c->dStop, 0, 4 * sizeof(int), c->stream));
@@ -342,6 +349,7 @@ int relayoutAfterOverflow(ipic_ctx* c, int outGen, int failedStep) {
 	int stop[4];
 	CK(cudaMemcpy(stop, c->dStop, sizeof stop, cudaMemcpyDeviceToHost));
 	// swap in the new storage
+	fresh.armed = false;
 	freeParticleBuffers(c);
 	cudaFree(c->dCellStart);
 	c->buf[0] = nb[0]; c->buf[1] = nb[1]; c->dTag = ntag; c->dCellStart = dNewStart; c->slots = nslots; c->slotsNf = c->g.nf; c->hCellStart = newStart;
@@ -372,6 +380,9 @@ int convertToFullLayout(ipic_ctx* c) {
 } // namespace
 
 extern "C" {
+
+// settles a batch left by ipic_step_async (waits, repairs a cell-segment overflow, redoes the skipped steps); defined with ipic_sync
+static int settleAsync(ipic_ctx* c);
 
 const char* ipic_last_error(void) { return g_lastError.c_str(); }
 const char* ipic_version(void) { return "ipic3d_b200 0.1 (sm_100a)"; }
@@ -406,7 +417,9 @@ int ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, 
 	CK(cudaGetDeviceCount(&ndev));
 	if (device < 0 || device >= ndev) return fail(IPIC_ERR_CUDA, "CUDA device %d not available (%d devices)", device, ndev);
 	CK(cudaSetDevice(device));
-	ipic_ctx* c = new ipic_ctx();
+	// a failure below (CK returns) must not leak the half-built context
+	struct Guard { ipic_ctx* c; ~Guard() { if (c) ipic_destroy(c); } } guard{ new ipic_ctx() };
+	ipic_ctx* c = guard.c;
 	c->device = device; c->rank = rank; c->nranks = nranks; c->props = *props;
 	fillGeometry(c);
 	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -450,6 +463,7 @@ int ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, 
 		CK(cudaMallocHost(&c->hStop, 4 * sizeof(int)));
 		CK(cudaEventCreateWithFlags(&c->evStepDone, cudaEventDisableTiming));
 	}
+	guard.c = nullptr;
 	*out = c;
 	return IPIC_OK;
 }
@@ -565,6 +579,7 @@ int establishLayout(ipic_ctx* c, const std::vector<int64_t>& need, int nf, doubl
 int ipic_upload_cells(ipic_ctx* c, const uint64_t* counts, const double* aos) {
 	if (!c || !counts) return fail(IPIC_ERR_ARG, "null argument");
 	CK(cudaSetDevice(c->device));
+	{ int rcA = settleAsync(c); if (rcA) return rcA; }
 	const int nOwned = ownedCells(c);
 	std::vector<int64_t> need((size_t)nOwned), aosStart((size_t)nOwned + 1, 0);
 	for (int i = 0; i < nOwned; i++) {
@@ -606,6 +621,7 @@ int ipic_upload_cells(ipic_ctx* c, const uint64_t* counts, const double* aos) {
 int ipic_generate_uniform(ipic_ctx* c, uint64_t numParticles) {
 	if (!c) return fail(IPIC_ERR_ARG, "null context");
 	CK(cudaSetDevice(c->device));
+	{ int rcA = settleAsync(c); if (rcA) return rcA; }
 	const Geometry& g = c->g;
 	const uint64_t numCells = (uint64_t)g.nx * g.ny * g.nz;
 	if (numParticles / numCells + 1 > 0x3fffffffu) return fail(IPIC_ERR_ARG, "%llu particles over %llu cells exceed 2^30 per cell", (unsigned long long)numParticles, (unsigned long long)numCells);
@@ -627,6 +643,7 @@ int ipic_generate_uniform(ipic_ctx* c, uint64_t numParticles) {
 int ipic_cell_counts(ipic_ctx* c, uint64_t* counts) {
 	if (!c || !counts) return fail(IPIC_ERR_ARG, "null argument");
 	CK(cudaSetDevice(c->device));
+	{ int rcA = settleAsync(c); if (rcA) return rcA; }
 	std::vector<int> owned;
 	int rc = fetchOwnedCounts(c, c->dCount, owned);
 	if (rc) return rc;
@@ -647,6 +664,7 @@ int ipic_total_particles(ipic_ctx* c, uint64_t* total) {
 int ipic_download_cells(ipic_ctx* c, uint64_t* counts, double* aos, uint64_t capacity) {
 	if (!c || !counts) return fail(IPIC_ERR_ARG, "null argument");
 	CK(cudaSetDevice(c->device));
+	{ int rcA = settleAsync(c); if (rcA) return rcA; }
 	std::vector<int> owned;
 	int rc = fetchOwnedCounts(c, c->dCount, owned);
 	if (rc) return rc;
@@ -669,6 +687,7 @@ int ipic_download_cells(ipic_ctx* c, uint64_t* counts, double* aos, uint64_t cap
 int ipic_upload_fields(ipic_ctx* c, const double* field, const double* bc, const double* J) {
 	if (!c) return fail(IPIC_ERR_ARG, "null context");
 	CK(cudaSetDevice(c->device));
+	{ int rcA = settleAsync(c); if (rcA) return rcA; }
 	if (field) {
 		int rc = ensureStage(c, c->nField * 9);
 		if (rc) return rc;
@@ -685,6 +704,7 @@ int ipic_upload_fields(ipic_ctx* c, const double* field, const double* bc, const
 int ipic_download_fields(ipic_ctx* c, double* field, double* bc, double* J) {
 	if (!c) return fail(IPIC_ERR_ARG, "null context");
 	CK(cudaSetDevice(c->device));
+	{ int rcA = settleAsync(c); if (rcA) return rcA; }
 	CK(cudaStreamSynchronize(c->stream));
 	if (field) {
 		int rc = ensureStage(c, c->nField * 9);
@@ -1210,6 +1230,13 @@ int runSlabSteps(ipic_ctx** ctxs, int n, uint64_t numSteps, uint32_t flags, doub
 			bool recovered = false;
 			int rc = confirmSlabStep(ctxs[r], &recovered);
 			if (rc) return rc;
+			if (recovered && f.fuseDeposit) {
+				// PH_FIELDS of the failed step was queued behind its import and did nothing (every kernel returns on the stop
+				// flag): the all-gathered corner sums of that step are still in dCellJ (the next step's movers, which would
+				// overwrite them, were skipped as well), so build J and advance the fields now, before those movers run again
+				rc = finishCurrent(ctxs[r]); if (rc) return rc;
+				fieldPhase(ctxs[r], f);
+			}
 			// the launches of the current step that were queued behind the failure did nothing: queue them again
 			if (recovered) for (int q = 0; q < uptoPhase; q++) { rc = slabPhase(ctxs[r], q, f, stepIndex); if (rc) return rc; }
 		}
@@ -1289,17 +1316,72 @@ static int checkSoloStep(ipic_ctx* c, uint32_t flags) {
 	return IPIC_OK;
 }
 
+// Waits for a batch of single-GPU steps whose first step started from generation `genAtStart`, and repairs it if an
+// import ran out of room: re-layout, redo that import, enqueue the steps that were skipped behind it, and so on until
+// all `numSteps` are done.  msFirst / msRest (may be null) accumulate the device time between the three events.
+static int finishSingleBatch(ipic_ctx* c, int genAtStart, uint64_t numSteps, uint32_t flags, cudaEvent_t* ev, float* msFirst, float* msRest) {
+	bool firstBatch = true;
+	for (;;) {
+		CK(cudaStreamSynchronize(c->stream));
+		if (ev) {
+			float a = 0, b = 0;
+			CK(cudaEventElapsedTime(&a, ev[0], ev[1]));
+			CK(cudaEventElapsedTime(&b, ev[1], ev[2]));
+			if (firstBatch) { *msFirst += a; *msRest += b; } else { *msRest += a + b; }      // only the very first step counts as "first"
+		}
+		firstBatch = false;
+		if (c->profiling) { int rc = drainProfile(c); if (rc) return rc; }
+		int stop[4];
+		CK(cudaMemcpy(stop, c->dStop, sizeof stop, cudaMemcpyDeviceToHost));
+		if (!stop[0]) return IPIC_OK;
+		// import of step `stop[1]` of this batch overflowed; later steps were skipped on the device
+		const int failed = stop[1];
+		const int outGen = genAtStart ^ ((failed + 1) & 1);
+		int rc = relayoutAfterOverflow(c, outGen, failed);
+		if (rc) return rc;
+		c->relayouts++;
+		c->cur = outGen;
+		if ((uint64_t)failed + 1 >= numSteps) return IPIC_OK;
+		numSteps -= (uint64_t)failed + 1;
+		genAtStart = c->cur;
+		if (ev) CK(cudaEventRecord(ev[0], c->stream));
+		rc = enqueueSteps(c, 0, 1, flags);
+		if (rc) return rc;
+		if (ev) CK(cudaEventRecord(ev[1], c->stream));
+		rc = enqueueSteps(c, 1, numSteps - 1, flags);
+		if (rc) return rc;
+		if (ev) CK(cudaEventRecord(ev[2], c->stream));
+	}
+}
+
+// A batch enqueued by ipic_step_async is settled before anything else looks at / changes the context's state.
+static int settleAsync(ipic_ctx* c) {
+	if (!c || c->asyncSteps == 0) return IPIC_OK;
+	CK(cudaSetDevice(c->device));
+	const uint64_t n = c->asyncSteps;
+	c->asyncSteps = 0;
+	return finishSingleBatch(c, c->asyncGenAtStart, n, c->asyncFlags, nullptr, nullptr, nullptr);
+}
+
 int ipic_step_async(ipic_ctx* c, uint64_t numSteps, uint32_t flags) {
 	int rc = checkSoloStep(c, flags);
 	if (rc) return rc;
 	if (c->nranks > 1) return fail(IPIC_ERR_ARG, "ipic_step_async is for single-GPU contexts: slab steps confirm every step on the host (ipic_step)");
 	CK(cudaSetDevice(c->device));
-	return enqueueSteps(c, 0, numSteps, flags);
+	if (c->asyncSteps && c->asyncFlags != flags) { rc = settleAsync(c); if (rc) return rc; }
+	if (c->asyncSteps == 0) { c->asyncGenAtStart = c->cur; c->asyncFlags = flags; }
+	// steps carry their index within the pending batch so that ipic_sync can locate an overflow
+	rc = enqueueSteps(c, c->asyncSteps, numSteps, flags);
+	if (rc) return rc;
+	c->asyncSteps += numSteps;
+	return IPIC_OK;
 }
 
 int ipic_sync(ipic_ctx* c) {
 	if (!c) return fail(IPIC_ERR_ARG, "null context");
 	CK(cudaSetDevice(c->device));
+	int rc = settleAsync(c);
+	if (rc) return rc;
 	CK(cudaStreamSynchronize(c->stream));
 	return IPIC_OK;
 }
@@ -1310,39 +1392,23 @@ int ipic_step(ipic_ctx* c, uint64_t numSteps, uint32_t flags, double* tFirst, do
 	{ int rc = checkSoloStep(c, flags); if (rc) return rc; }
 	if (numSteps == 0) return IPIC_OK;
 	CK(cudaSetDevice(c->device));
+	{ int rc = settleAsync(c); if (rc) return rc; }
 	if (c->nranks > 1) return runSlabSteps(&c, 1, numSteps, flags, tFirst, tRest);
 	cudaEvent_t ev[3];
 	for (auto& e : ev) CK(cudaEventCreate(&e));
-	uint64_t done = 0;
 	float msFirst = 0, msRest = 0;
-	while (done < numSteps) {
+	{
 		const int genAtStart = c->cur;
-		const uint64_t batch = numSteps - done;
 		CK(cudaEventRecord(ev[0], c->stream));
 		int rc = enqueueSteps(c, 0, 1, flags);
 		if (rc) return rc;
 		CK(cudaEventRecord(ev[1], c->stream));
 		// the remaining steps carry their index within this batch so that an overflow can be located
-		rc = enqueueSteps(c, 1, batch - 1, flags);
+		rc = enqueueSteps(c, 1, numSteps - 1, flags);
 		if (rc) return rc;
 		CK(cudaEventRecord(ev[2], c->stream));
-		CK(cudaStreamSynchronize(c->stream));
-		float a = 0, b = 0;
-		CK(cudaEventElapsedTime(&a, ev[0], ev[1]));
-		CK(cudaEventElapsedTime(&b, ev[1], ev[2]));
-		if (done == 0) { msFirst += a; msRest += b; } else { msRest += a + b; }
-		if (c->profiling) { rc = drainProfile(c); if (rc) return rc; }
-		int stop[4];
-		CK(cudaMemcpy(stop, c->dStop, sizeof stop, cudaMemcpyDeviceToHost));
-		if (!stop[0]) { done = numSteps; break; }
-		// import of step `stop[1]` of this batch overflowed; later steps were skipped on the device
-		const int failed = stop[1];
-		const int outGen = genAtStart ^ ((failed + 1) & 1);
-		rc = relayoutAfterOverflow(c, outGen, failed);
+		rc = finishSingleBatch(c, genAtStart, numSteps, flags, ev, &msFirst, &msRest);
 		if (rc) return rc;
-		c->relayouts++;
-		c->cur = outGen;
-		done += (uint64_t)failed + 1;
 	}
 	for (auto& e : ev) cudaEventDestroy(e);
 	if (tFirst) *tFirst = msFirst / 1000.0;
@@ -1393,6 +1459,7 @@ int ipic_group_step(ipic_ctx** ctxs, int n, uint64_t numSteps, uint32_t flags, d
 int ipic_count_misplaced(ipic_ctx* c, uint64_t* misplaced) {
 	if (!c || !misplaced) return fail(IPIC_ERR_ARG, "null argument");
 	CK(cudaSetDevice(c->device));
+	{ int rcA = settleAsync(c); if (rcA) return rcA; }
 	unsigned long long* d = nullptr;
 	CK(cudaMalloc(&d, sizeof(unsigned long long)));
 	CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), c->stream));
@@ -1409,6 +1476,7 @@ int ipic_count_misplaced(ipic_ctx* c, uint64_t* misplaced) {
 int ipic_diagnostics(ipic_ctx* c, double* out4) {
 	if (!c || !out4) return fail(IPIC_ERR_ARG, "null argument");
 	CK(cudaSetDevice(c->device));
+	{ int rcA = settleAsync(c); if (rcA) return rcA; }
 	const int64_t pairs = (int64_t)std::max(1, c->g.ncellsLocal) + kFieldEnergyChunks + 2;
 	int rc = ensureStage(c, 2 * pairs);
 	if (rc) return rc;

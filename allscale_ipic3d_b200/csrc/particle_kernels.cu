@@ -1294,14 +1294,24 @@ static size_t move_smem_bytes(int nf, int stages) {
 	return (size_t)stages * kBlock * nf * sizeof(double);
 }
 
+// Opt-in to more than 48 KiB of dynamic shared memory.  The attribute belongs to the (kernel, device) pair, so it is
+// set once per device the kernel is launched on (in-process groups drive several devices from one process); `mask`
+// is the per-instantiation set of devices already configured.  A failure stays in cudaGetLastError for the caller's
+// check after the launch.
+template<typename Kernel>
+static void optin_dynamic_smem(Kernel kernel, size_t bytes, unsigned long long& mask) {
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) return;
+	const unsigned long long bit = 1ull << (dev & 63);
+	if (mask & bit) return;
+	if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess) mask |= bit;
+}
+
 template<int NF, bool INTERP, bool DEPOSIT, bool MIGRATE, bool PUSH>
 static void launch_move_k(const MoveArgs& a, int grid, cudaStream_t st) {
-	static bool configured = false;                  // opt in to > 48 KiB of dynamic shared memory once per instantiation
+	static unsigned long long configured = 0;        // devices on which this instantiation has its shared-memory opt-in
 	auto kernel = k_move<NF, INTERP, DEPOSIT, MIGRATE, PUSH>;
-	if (!configured) {
-		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)move_smem_bytes(NF, kMaxStages));
-		configured = true;
-	}
+	optin_dynamic_smem(kernel, move_smem_bytes(NF, kMaxStages), configured);
 	const int stages = std::max(1, std::min(a.stages, kMaxStages));
 	kernel<<<grid, kBlock, move_smem_bytes(NF, stages), st>>>(a.g, a.in, a.out, a.cellStart, a.countIn, a.countOut, a.nLeave, a.tag,
 	                                                          a.fieldEB, a.cellJ, a.stopFlag, a.zBegin, a.zCount, stages);
@@ -1309,12 +1319,9 @@ static void launch_move_k(const MoveArgs& a, int grid, cudaStream_t st) {
 
 template<int NF, bool MIGRATE>
 static void launch_move_ws(const MoveArgs& a, int grid, cudaStream_t st) {
-	static bool configured = false;
+	static unsigned long long configured = 0;
 	auto kernel = k_move_ws<NF, MIGRATE>;
-	if (!configured) {
-		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)move_smem_bytes(NF, kMaxStages));
-		configured = true;
-	}
+	optin_dynamic_smem(kernel, move_smem_bytes(NF, kMaxStages), configured);
 	const int stages = std::max(1, std::min(a.stages, kMaxStages));
 	kernel<<<grid, kBlock + 32, move_smem_bytes(NF, stages), st>>>(a.g, a.in, a.out, a.cellStart, a.countIn, a.countOut, a.nLeave, a.tag,
 	                                                               a.cellJ, a.stopFlag, a.zBegin, a.zCount, stages);
@@ -1349,10 +1356,10 @@ static void launch_move_i(const MoveArgs& a, cudaStream_t st) {
 
 template<int NF, bool INTERP, bool DEPOSIT, bool MIGRATE>
 static void launch_chunk_k(const MoveArgs& a, cudaStream_t st) {
-	static bool configured = false;
+	static unsigned long long configured = 0;
 	auto kernel = k_move_chunk<NF, INTERP, DEPOSIT, MIGRATE>;
 	const size_t smem = (size_t)kChunk * NF * sizeof(double);
-	if (!configured) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+	optin_dynamic_smem(kernel, smem, configured);
 	cudaMemsetAsync(a.chunkStatus + a.chunkFirst, 0, (size_t)a.chunkCount * sizeof(unsigned long long), st);
 	cudaMemsetAsync(a.chunkTicket, 0, sizeof(unsigned), st);
 	kernel<<<a.chunkCount, kBlock, smem, st>>>(a.g, a.in, a.out, a.cellStart, a.countIn, a.countOut, a.nLeave, a.tag, a.fieldEB, a.cellJ, a.chunkJ,
