@@ -450,6 +450,63 @@ def slab_of(counts, aos, nxy, nz, rank, world):
     return mine, np.asarray(aos).reshape(-1, 8)[idx]
 
 
+class Deck:
+    """An input deck as ``ipic3d <deck>`` sets it up (host mirror's EarthDeck), generated piecewise: phase 1 of initCells
+    (every cell's population) runs once at open, after which any range of z-planes can be produced on its own --
+    what one rank of a multi-GPU run needs.  Bit-identical to the reference's universe (tests/test_host_mirror.py)."""
+
+    def __init__(self, deck_path):
+        lib = load_host_library()
+        lib.ipic_host_deck_open.restype = C.c_void_p
+        self.lib = lib
+        self.props = Props()
+        cycles, n = C.c_uint64(0), C.c_int64(0)
+        self.h = C.c_void_p(lib.ipic_host_deck_open(deck_path.encode(), C.byref(self.props), C.byref(cycles), C.byref(n)))
+        self.ncycles, self.num_particles = int(cycles.value), int(n.value)
+
+    def close(self):
+        if self.h:
+            self.lib.ipic_host_deck_close(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def counts(self, z_begin=0, z_count=None):
+        z_count = int(self.props.size[2]) - z_begin if z_count is None else z_count
+        out = np.zeros(int(self.props.size[0] * self.props.size[1]) * z_count, dtype=np.uint64)
+        if self.lib.ipic_host_deck_counts(self.h, C.c_int(z_begin), C.c_int(z_count), _up(out)):
+            raise IpicError(-1, "ipic_host_deck_counts: bad arguments")
+        return out
+
+    def particles_into(self, aos_ptr, z_begin=0, z_count=None, threads=0):
+        z_count = int(self.props.size[2]) - z_begin if z_count is None else z_count
+        if self.lib.ipic_host_deck_particles(self.h, C.c_int(z_begin), C.c_int(z_count), C.c_void_p(aos_ptr), C.c_int(threads)):
+            raise IpicError(-1, "ipic_host_deck_particles: bad arguments")
+
+    def slab(self, rank=0, world=1):
+        """(counts, particles) of z-slab `rank` of `world` in slab order."""
+        lz = int(self.props.size[2]) // world
+        counts = self.counts(rank * lz, lz)
+        aos = np.empty((int(counts.sum()), 8), dtype=np.float64)
+        if len(aos):
+            self.particles_into(aos.ctypes.data, rank * lz, lz)
+        return counts, aos
+
+
+def deck_slab_pinned(deck_path, rank, world, torch):
+    """z-slab `rank` of `world` of the deck's universe generated straight into pinned host memory: (props, counts, tensor)."""
+    with Deck(deck_path) as d:
+        lz = int(d.props.size[2]) // world
+        counts = d.counts(rank * lz, lz)
+        host = torch.empty((int(counts.sum()), 8), dtype=torch.float64).pin_memory()
+        d.particles_into(host.data_ptr(), rank * lz, lz)
+        return Props.from_other(d.props), counts, host
+
+
 def dipole_universe(deck_path, grid, per_dim):
     """The reference's `ipic3d <deck>` universe (main()'s Earth set-up, two-phase initCells) built by the host C++ mirror,
     with the deck's grid replaced by grid^3 cells (box length scaled to keep the cell width) and per_dim^3 particles per cell."""

@@ -241,6 +241,7 @@ void fillGeometry(ipic_ctx* c) {
 	g.r2planet = p.planetRadius * p.planetRadius;
 	g.magTemp = -p.externalMagneticField[2] * std::pow(p.planetRadius, 3);   // host libm, as the reference (cell.h:919)
 	g.pic = M_PI * p.speedOfLight;                                           // cell.h:949
+	g.picSafe = g.pic * (1.0 - 1e-6);
 	g.vol = p.cellWidth[0] * p.cellWidth[1] * p.cellWidth[2];
 	g.nf = kFields; g.uq = 0.0; g.uqom = 0.0;
 }
@@ -253,7 +254,7 @@ void pickTileShape(const ipic_ctx* c, bool deposit, bool pushes, int& stages) {
 	const int64_t avg = c->meanPopulation;
 	const int64_t tile = 128;
 	// fused deposit, warp-specialised (k_move_ws): a deep ring decouples the deposit warp from the push warps (sweep: 8 > 6 > 4)
-	const bool ws = deposit && pushes && c->g.magTemp == 0.0;      // launch_move's choice of k_move_ws
+	const bool ws = move_uses_ws(c->g, deposit, !pushes, true);    // launch_move's choice of k_move_ws (callers pass pushes = !interpolate)
 	// (8 stages of the 8-field layout are 64 KiB: six keep four CTAs per SM)
 	stages = (int)std::max<int64_t>(1, std::min<int64_t>((avg + avg / 8 + tile - 1) / tile, ws ? (c->g.nf == kFields ? 6 : 8) : (deposit ? 4 : 2)));
 	if (const char* e = std::getenv("IPIC_STAGES")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) stages = v; }   // tuning knob

@@ -183,6 +183,7 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	// cell coordinate first); without an external dipole moment the analytic field is +-0 everywhere
 	const bool wallCell = cx == 0 || cy == 0 || cz == 0 || cx == g.nx - 1 || cy == g.ny - 1 || cz == g.nz - 1;
 	const bool fieldFree = !INTERP && g.magTemp == 0.0 && g.pic > 0.0 && g.dt > 0.0 && g.dt < 1e100;
+	const bool plainDipole = !INTERP && fabs(g.magTemp) > 1e-100 && fabs(g.magTemp) < 1e100 && g.pic > 0.0 && g.dt > 0.0 && g.dt < 1e100;
 
 	int kept = 0, left = 0, par = 0;
 	uint32_t phase = 0;
@@ -283,9 +284,7 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 						const Vec3 B = trilinear(sCorner + 3, 6, rx, ry, rz, g.vol);
 						push_with_fields(g, px[k], py[k], pz[k], vx[k], vy[k], vz[k], pm[k], E, B);
 					} else if (!(fieldFree && field_free_push(g, px[k], py[k], pz[k], vx[k], vy[k], vz[k], pm[k]))) {
-						Vec3 E, B;
-						dipole_field(g, px[k], py[k], pz[k], E, B);
-						push_with_fields(g, px[k], py[k], pz[k], vx[k], vy[k], vz[k], pm[k], E, B);
+						dipole_push(g, plainDipole, px[k], py[k], pz[k], vx[k], vy[k], vz[k], pm[k]);
 					}
 					code[k] = MIGRATE ? classify(g, wallCell, cx, cy, cz, ctr, px[k], py[k], pz[k], vx[k], vy[k], vz[k]) : 13u;
 				}
@@ -492,6 +491,7 @@ k_move_ws(const Geometry g, const ParticleArrays in, const ParticleArrays out, c
 	// ================= push warps =================
 	const bool wallCell = cx == 0 || cy == 0 || cz == 0 || cx == g.nx - 1 || cy == g.ny - 1 || cz == g.nz - 1;
 	const bool fieldFree = g.magTemp == 0.0 && g.pic > 0.0 && g.dt > 0.0 && g.dt < 1e100;
+	const bool plainDipole = fabs(g.magTemp) > 1e-100 && fabs(g.magTemp) < 1e100 && g.pic > 0.0 && g.dt > 0.0 && g.dt < 1e100;
 	const unsigned lt = (1u << lane) - 1u;
 	int kept = 0, left = 0, par = 0, s = 0;
 	uint32_t phase = 0;
@@ -505,11 +505,7 @@ k_move_ws(const Geometry g, const ParticleArrays in, const ParticleArrays out, c
 			px = p[0]; py = p[32]; pz = p[64];
 			vx = p[96]; vy = p[128]; vz = p[160];
 			if (NF == 8) { pq = p[192]; pm = p[224]; } else { pq = g.uq; pm = g.uqom; }
-			if (!(fieldFree && field_free_push(g, px, py, pz, vx, vy, vz, pm))) {
-				Vec3 E, B;
-				dipole_field(g, px, py, pz, E, B);
-				push_with_fields(g, px, py, pz, vx, vy, vz, pm, E, B);
-			}
+			if (!(fieldFree && field_free_push(g, px, py, pz, vx, vy, vz, pm))) dipole_push(g, plainDipole, px, py, pz, vx, vy, vz, pm);
 			code = MIGRATE ? classify(g, wallCell, cx, cy, cz, ctr, px, py, pz, vx, vy, vz) : 13u;
 		}
 		const unsigned bs = __ballot_sync(0xffffffffu, code == 13u);
@@ -649,6 +645,7 @@ k_move_chunk(const Geometry g, const ParticleArrays in, const ParticleArrays out
 	const double* ctr = sGeo + 3;
 	const bool wallCell = cx == 0 || cy == 0 || cz == 0 || cx == g.nx - 1 || cy == g.ny - 1 || cz == g.nz - 1;
 	const bool fieldFree = !INTERP && g.magTemp == 0.0 && g.pic > 0.0 && g.dt > 0.0 && g.dt < 1e100;
+	const bool plainDipole = !INTERP && fabs(g.magTemp) > 1e-100 && fabs(g.magTemp) < 1e100 && g.pic > 0.0 && g.dt > 0.0 && g.dt < 1e100;
 	const unsigned lt = (1u << lane) - 1u;
 
 	if (cnt > 0) {
@@ -715,9 +712,7 @@ k_move_chunk(const Geometry g, const ParticleArrays in, const ParticleArrays out
 				const Vec3 B = trilinear(sCorner + 3, 6, rx, ry, rz, g.vol);
 				push_with_fields(g, px, py, pz, vx, vy, vz, pm, E, B);
 			} else if (!(fieldFree && field_free_push(g, px, py, pz, vx, vy, vz, pm))) {
-				Vec3 E, B;
-				dipole_field(g, px, py, pz, E, B);
-				push_with_fields(g, px, py, pz, vx, vy, vz, pm, E, B);
+				dipole_push(g, plainDipole, px, py, pz, vx, vy, vz, pm);
 			}
 			code = MIGRATE ? classify(g, wallCell, cx, cy, cz, ctr, px, py, pz, vx, vy, vz) : 13u;
 			p[0] = px; p[32] = py; p[64] = pz; p[96] = vx; p[128] = vy; p[160] = vz;
@@ -1281,6 +1276,16 @@ __global__ void k_selftest_division(uint64_t n, uint64_t seed, unsigned long lon
 	div3_ge1(x, y, z, den);
 	if (__double_as_longlong(x) != __double_as_longlong(wx) || __double_as_longlong(y) != __double_as_longlong(wy) ||
 	    __double_as_longlong(z) != __double_as_longlong(wz)) atomicAdd(bad, 1ull);
+	// the quotient magTemp / |p|^5 of dipole_push: any numerator and denominator with magnitudes in (1e-100, 1e100)
+	auto wide = [&]() {
+		const uint64_t r = next();
+		const double m = 1.0 + (double)(next() >> 11) * (1.0 / 9007199254740992.0);
+		const int e = (int)((r >> 8) % 661) - 330;
+		return ((r & 32) ? -m : m) * exp2((double)e);
+	};
+	const double num = wide(), dd = fabs(wide());
+	const double want = num / dd, got = div_by_rcp(num, dd, rcp_newton(dd));
+	if (__double_as_longlong(want) != __double_as_longlong(got)) atomicAdd(bad, 1ull);
 }
 
 void launch_selftest_division(uint64_t n, uint64_t seed, unsigned long long* bad, cudaStream_t st) {
@@ -1332,14 +1337,24 @@ static bool use_warp_specialised() {
 	if (v < 0) { const char* e = std::getenv("IPIC_WS"); v = e ? (std::atoi(e) != 0) : 1; }
 	return v != 0;
 }
+// tuning knob: the warp-specialised kernel for the analytic dipole as well (IPIC_WS_DIPOLE=1)
+static bool ws_for_dipole() {
+	static int v = -1;
+	if (v < 0) { const char* e = std::getenv("IPIC_WS_DIPOLE"); v = e ? (std::atoi(e) != 0) : 0; }
+	return v != 0;
+}
+
+// the deposit warp pays off when the push is light (field-free plasma: the push warps are integer / issue bound); with the
+// analytic dipole every push carries a pow and ~150 FP64 operations, and the four-warp kernel's 5 CTAs/SM of pushers win
+bool move_uses_ws(const Geometry& g, bool deposit, bool interpolate, bool push) {
+	return deposit && !interpolate && push && (g.magTemp == 0.0 || ws_for_dipole()) && use_warp_specialised();
+}
 
 template<int NF, bool INTERP, bool DEPOSIT>
 static void launch_move_t(const MoveArgs& a, cudaStream_t st) {
 	const int grid = a.g.nx * a.g.ny * a.zCount;
 	if (grid == 0) return;
-	// the deposit warp pays off when the push is light (field-free plasma: the push warps are integer / issue bound); with the
-	// analytic dipole every push carries a pow and ~150 FP64 operations, the four-warp kernel's 5 CTAs/SM of pushers win (B200: 0.61 vs 0.63 ms)
-	if (DEPOSIT && !INTERP && a.push && a.g.magTemp == 0.0 && use_warp_specialised()) {
+	if (move_uses_ws(a.g, DEPOSIT, INTERP, a.push)) {
 		if (a.migrate) launch_move_ws<NF, true>(a, grid, st); else launch_move_ws<NF, false>(a, grid, st);
 		return;
 	}

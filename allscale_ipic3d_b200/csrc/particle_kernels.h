@@ -43,6 +43,8 @@ struct ImportArgs {
 };
 
 void launch_move(const MoveArgs& a, cudaStream_t st);
+// does launch_move run the warp-specialised kernel (k_move_ws: a fifth warp deposits) for these switches?
+bool move_uses_ws(const Geometry& g, bool deposit, bool interpolate, bool push);
 // `commit`: also raise the stop flag if any import pass of this step overflowed a cell segment
 void launch_import(const ImportArgs& a, bool commit, cudaStream_t st);
 // z-slab exchange: pack both faces of the slab into their messages (3 launches)

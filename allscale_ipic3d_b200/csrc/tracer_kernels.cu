@@ -4,7 +4,7 @@
 //
 // One thread per particle for all T steps: the state lives in registers, HBM sees 64 B per particle once and
 // one 32-bit atomic per (particle, frame).  Integer atomics commute, so the frames are deterministic.  The
-// arithmetic is the mover's (ipic_device.cuh: dipole_field, push_with_fields -- same expressions as
+// arithmetic is the mover's (ipic_device.cuh: dipole_push -- same expressions as
 // pic_tracer.cxx:102-124), compiled with -fmad=false.
 #include "tracer_kernels.h"
 
@@ -32,12 +32,11 @@ k_trace(const Geometry g, const double* __restrict__ aos, int64_t n, int T, int 
 	}
 	if (px > hx || px < lx || py > hy || py < ly || pz > hz || pz < lz) return;         // :95-98
 
+	const bool plainDipole = fabs(g.magTemp) > 1e-100 && fabs(g.magTemp) < 1e100 && g.pic > 0.0 && g.dt > 0.0 && g.dt < 1e100;
 	for (int t = 0; t < T; t++) {
 		// getCellCoordinates (hdr/cell.h:63-66): truncation of (p - origin) / width
 		const long long cx = (long long)((px - lx) / g.w[0]), cy = (long long)((py - ly) / g.w[1]), cz = (long long)((pz - lz) / g.w[2]);
-		Vec3 E, B;
-		dipole_field(g, px, py, pz, E, B);                                              // :106-112
-		push_with_fields(g, px, py, pz, vx, vy, vz, qom, E, B);                         // :114-127
+		dipole_push(g, plainDipole, px, py, pz, vx, vy, vz, qom);                       // :106-127 (dipole field, sub-cycling, Boris)
 		// periodic wrap (:129-133)
 		if (px > hx) px -= sx;
 		if (px < lx) px += sx;

@@ -288,6 +288,72 @@ def parity_gate(args, np, dist, ipic, capi, rank, world, local, flags):
             ctx.comm_init(bcast(ipic.Context.comm_unique_id() if rank == 0 else None))
         return ctx
 
+    # ---- the medium.inp deck: truncated-step parity at full size (SURVEY 8d "M verified on a truncated step range") -------
+    if args.workload == "medium":
+        deck = os.path.join(ROOT, "tests", "golden", "inputs", "medium.inp")
+        shm = "/dev/shm/ipic_gate_%d" % os.getppid() if world > 1 else "/dev/shm/ipic_gate_%d" % os.getpid()
+        shm = bcast(shm)
+        have_ref, n_ref = True, 0
+        if rank == 0:
+            threaded = harness.Ref.available(True)
+            have_ref = harness.Ref.available(threaded) and host_memory_allows(262144000)
+            if have_ref:
+                r = harness.Ref.from_inp(deck, threaded=threaded)
+                t = r.step(steps)
+                if not args.no_cpu_baseline:
+                    cpu = {"value": steps * r.num_particles / t, "unit": UNIT, "cores": r.threads() if threaded else 1, "kind": "reference",
+                           "sample": "the whole workload: medium.inp universe built by the reference's main() set-up, first %d steps of its simulateSteps "
+                                     "(includes the first, cold step), %d host threads" % (steps, r.threads() if threaded else 1)}
+                np.save(shm + "_counts.npy", r.counts())
+                n_ref = r.total()
+                mm = np.lib.format.open_memmap(shm + "_particles.npy", mode="w+", dtype=np.float64, shape=(n_ref, 8))
+                r.lib.ref_get_particles(r.h, mm.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+                mm.flush(); del mm
+                r.close()
+        have_ref = bcast(have_ref)
+        if not have_ref:
+            return {"ran": False, "ok": None, "why": "oracle/_ref not built or not enough host memory for the reference's 16.8 GB universe"}, None
+        props, counts, host = capi.deck_slab_pinned(deck, rank, world, __import__("torch"))
+        nz = int(props.size[2]); nxy = int(props.size[0] * props.size[1]); lz = nz // world
+        with slab_ctx(props) as ctx:
+            ctx.upload_cells_ptr(counts, host.data_ptr())
+            del host
+            ctx.step(steps, flags)
+            got_c, got_p = ctx.download_cells()
+        ref_counts = np.load(shm + "_counts.npy")
+        ref_p = np.load(shm + "_particles.npy", mmap_mode="r")
+        cells = (np.arange(nxy)[:, None] * nz + rank * lz + np.arange(lz)[None, :]).reshape(-1)
+        same = bool(np.array_equal(got_c, ref_counts[cells]))
+        ep = ev = 0.0
+        checked = 0
+        if same:
+            ref_start = np.concatenate([[0], np.cumsum(ref_counts)]).astype(np.int64)
+            my_start = np.concatenate([[0], np.cumsum(got_c)]).astype(np.int64)
+            for k in range(0, len(cells), 61):                       # every 61st cell of the slab, all of its particles
+                a = got_p[my_start[k]:my_start[k + 1]]
+                b = np.asarray(ref_p[ref_start[cells[k]]:ref_start[cells[k] + 1]])
+                if len(a):
+                    ep = max(ep, harness.norm_rel_err(a[:, 0:3], b[:, 0:3])); ev = max(ev, harness.norm_rel_err(a[:, 3:6], b[:, 3:6]))
+                    checked += len(a)
+        parts = gather((same, ep, ev, checked, int(got_c.sum())))
+        del ref_p
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            for f in ("_counts.npy", "_particles.npy"):
+                try:
+                    os.unlink(shm + f)
+                except OSError:
+                    pass
+        ok = all(p[0] for p in parts) and max(p[1] for p in parts) <= 1e-12 and max(p[2] for p in parts) <= 1e-12
+        gate["checks"].append({"case": "medium.inp (64^3 cells, 262144000 particles), first %d steps, %d GPU(s)%s vs the reference's own run of the deck" % (
+                                   steps, world, " as NCCL z-slabs" if world > 1 else ""),
+                               "counts_equal_all_262144_cells": all(p[0] for p in parts), "particles_alive": int(sum(p[4] for p in parts)),
+                               "particles_compared": int(sum(p[3] for p in parts)), "max_norm_rel_err_pos": max(p[1] for p in parts),
+                               "max_norm_rel_err_vel": max(p[2] for p in parts), "tolerance": 1e-12})
+        gate["ok"] = bool(ok)
+        return gate, cpu
+
     # ---- (a) the uniform plasma ------------------------------------------------------------------
     if args.workload == "uniform":
         n_gate = args.particles_per_gpu * world if world == 1 else min(args.particles_per_gpu, 4_000_000) * world
@@ -426,7 +492,7 @@ def run_b200(args):
 
     # ---- parity gate (and, at N = 1, the cpu_baseline leg: the same reference run serves both) ------------------
     gate, cpu = {"ran": False, "ok": None, "why": "--no-parity-gate"}, None
-    if not args.no_parity_gate and args.workload == "uniform":
+    if not args.no_parity_gate and args.workload in ("uniform", "medium"):
         gate, cpu = parity_gate(args, np, dist, ipic, capi, rank, world, local, flags)
         if gate.get("ran") and not gate.get("ok"):
             if rank == 0:
@@ -575,7 +641,7 @@ def run_b200(args):
                                      "whole_protocol_value": 7 * n_total / max_over_ranks(t3 - t0), "upload_plus_warmup_s": max_over_ranks(t1 - t0),
                                      "download_s": max_over_ranks(t3 - t2)}}
 
-    if cpu is None and rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload in ("uniform", "medium"):
+    if cpu is None and rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "uniform":
         n_cpu = args.cpu_particles or n_total
         while n_cpu > 1_000_000 and not host_memory_allows(n_cpu):
             n_cpu //= 2

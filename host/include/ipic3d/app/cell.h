@@ -209,6 +209,58 @@ namespace ipic3d {
 		}
 	}
 
+	namespace detail {
+		// Phase 1 of the generic initCells (reference hdr/cell.h:506-594), sequential: histogram of 100 pseudo particles per
+		// cell, each standing for numParticles / (100 numCells) particles; what the truncation leaves over is spread evenly,
+		// the remainder over the first cells of the z-fastest flatten.  Returns the population of every cell.
+		template<typename Distribution>
+		std::vector<std::uint64_t> approximatePopulation(const UniverseProperties& properties, std::uint64_t numParticles, Distribution sampler) {
+			const coordinate_type grid = properties.size;
+			std::cout << "Approximating particle distribution ...\n";
+			const std::int64_t numCells = grid.x * grid.y * grid.z;
+			std::vector<std::uint64_t> population((std::size_t)numCells, 0);
+			const std::int64_t pseudoParticles = numCells * 100;
+			const std::uint64_t weight = numParticles / pseudoParticles;
+			for (std::int64_t i = 0; i < pseudoParticles; ++i) {
+				Particle p = sampler();
+				while (!isInsideUniverse(properties, p)) p = sampler();
+				const coordinate_type c = getCellCoordinates(properties, p);
+				population[(std::size_t)((c.x * grid.y + c.y) * grid.z + c.z)] += weight;
+			}
+			std::uint64_t sum = 0, hi = 0, lo = std::numeric_limits<std::uint64_t>::max();
+			for (std::uint64_t v : population) { sum += v; hi = std::max(hi, v); lo = std::min(lo, v); }
+			const std::int64_t missing = (std::int64_t)(numParticles - sum);
+			if (missing != 0) {
+				const int everywhere = (int)(missing / numCells);
+				const int firstCells = (int)(missing % numCells);
+				for (std::int64_t lin = 0; lin < numCells; ++lin) population[(std::size_t)lin] += everywhere + (lin < firstCells ? 1 : 0);
+			}
+			// (the reference prints the statistics of the uncorrected histogram here, hdr/cell.h:559-591)
+			std::cout << "Number of particles in cells (min/avg/max): " << lo << "/" << (sum / numCells) << "/" << hi << "\n";
+			return population;
+		}
+
+		// Phase 2 for ONE cell (reference hdr/cell.h:596-632): the distribution re-seeded with the cell's seed gives species and
+		// velocity, positions are uniform in the cell's box from their own engine, charge and mass are the proton's.
+		// Independent per cell, so a z-slab (or one GPU's share) can be generated without the rest of the universe.
+		template<typename Distribution>
+		void populateCell(const UniverseProperties& properties, const coordinate_type& pos, std::uint64_t n, const Distribution& sampler, Particle* out) {
+			const double e = 1.602176565e-19;      // elementary charge (C)
+			const double m = 1.672621777e-27;      // proton mass (kg)
+			const CellBox box = cellBox(properties, pos);
+			Distribution mine = sampler;
+			mine.seed(box.seed);
+			distribution::vector::uniform place(box.low, box.high, box.seed);
+			for (std::uint64_t i = 0; i < n; ++i) {
+				Particle p = mine();
+				p.position = place();
+				p.q = e;
+				p.qom = e / m;
+				out[i] = p;
+			}
+		}
+	}
+
 	// Any distribution (the `.inp` runs): per-cell populations follow a coarse Monte-Carlo estimate of the
 	// distribution's density, positions inside a cell are uniform, velocities and species come from the
 	// re-seeded distribution, charge and mass are the proton's.
@@ -216,54 +268,12 @@ namespace ipic3d {
 	Cells initCells(const UniverseProperties& properties, std::uint64_t numParticles, const Distribution& dist) {
 		const coordinate_type grid = properties.size;
 		Cells cells(grid);
-		Distribution sampler = dist;
-
-		const double e = 1.602176565e-19;      // elementary charge (C)
-		const double m = 1.672621777e-27;      // proton mass (kg)
-
-		std::cout << "Approximating particle distribution ...\n";
-
-		const std::int64_t numCells = grid.x * grid.y * grid.z;
-		std::vector<std::uint64_t> population((std::size_t)numCells, 0);
-		const std::int64_t pseudoParticles = numCells * 100;
-		const std::uint64_t weight = numParticles / pseudoParticles;
-
-		// phase 1 (sequential): histogram of 100 pseudo particles per cell, each standing for `weight` particles
-		for (std::int64_t i = 0; i < pseudoParticles; ++i) {
-			Particle p = sampler();
-			while (!isInsideUniverse(properties, p)) p = sampler();
-			population[cells.flatten(getCellCoordinates(properties, p))] += weight;
-		}
-		std::uint64_t sum = 0, hi = 0, lo = std::numeric_limits<std::uint64_t>::max();
-		for (std::uint64_t v : population) { sum += v; hi = std::max(hi, v); lo = std::min(lo, v); }
-		// what the histogram's truncation left over is spread evenly, the remainder over the first cells
-		const std::int64_t missing = (std::int64_t)(numParticles - sum);
-		if (missing != 0) {
-			const int everywhere = (int)(missing / numCells);
-			const int firstCells = (int)(missing % numCells);
-			for (std::int64_t lin = 0; lin < numCells; ++lin) population[(std::size_t)lin] += everywhere + (lin < firstCells ? 1 : 0);
-		}
-		// (the reference prints the statistics of the uncorrected histogram here, hdr/cell.h:559-591)
-		std::cout << "Number of particles in cells (min/avg/max): " << lo << "/" << (sum / numCells) << "/" << hi << "\n";
-
+		const std::vector<std::uint64_t> population = detail::approximatePopulation(properties, numParticles, dist);
 		std::cout << "Populating cells ...\n";
-
-		// phase 2 (independent per cell: own seed, own generators)
 		pfor(coordinate_type(0), grid, [&](const coordinate_type& pos) {
-			const detail::CellBox box = detail::cellBox(properties, pos);
-			Distribution mine = sampler;
-			mine.seed(box.seed);
-			distribution::vector::uniform place(box.low, box.high, box.seed);
 			Cell& cell = cells[pos];
-			const std::uint64_t n = population[cells.flatten(pos)];
-			cell.particles.reserve(n);
-			for (std::uint64_t i = 0; i < n; ++i) {
-				Particle p = mine();
-				p.position = place();
-				p.q = e;
-				p.qom = e / m;
-				cell.particles.push_back(p);
-			}
+			cell.particles.resize(population[cells.flatten(pos)]);
+			detail::populateCell(properties, pos, cell.particles.size(), dist, cell.particles.data());
 		});
 		return cells;
 	}

@@ -52,13 +52,20 @@ namespace ipic3d {
 			return c / std::sqrt(1.0 + (m * c * c) / K);
 		}
 
-		Universe createUniverse() const {
+		// 10 MeV protons in the inner 75 % box, generator seed 0 (ipic3d.cxx:72-83)
+		distribution::uniform_pos_normal_speed<> protons() const {
 			const double v = thermalSpeed();
 			const auto low = properties.origin + 0.125 * boxSize();
 			const auto high = low + 0.75 * boxSize();
-			const distribution::uniform_pos_normal_speed<> protons(low, high, Vector3<double>{ 0, 0, 0 }, Vector3<double>{ v, v, v });
-			return createUniverseFromDistribution(properties, init, numParticles, protons);
+			return distribution::uniform_pos_normal_speed<>(low, high, Vector3<double>{ 0, 0, 0 }, Vector3<double>{ v, v, v });
 		}
+
+		Universe createUniverse() const { return createUniverseFromDistribution(properties, init, numParticles, protons()); }
+
+		// The same universe piecewise, for callers that never hold all of it (one z-slab per GPU / per process):
+		// phase 1 of initCells once (cheap, sequential, identical everywhere), then any cell on its own.
+		std::vector<std::uint64_t> cellPopulations() const { return detail::approximatePopulation(properties, (std::uint64_t)numParticles, protons()); }
+		void populateCell(const coordinate_type& pos, std::uint64_t n, Particle* out) const { detail::populateCell(properties, pos, n, protons(), out); }
 	};
 
 } // namespace ipic3d

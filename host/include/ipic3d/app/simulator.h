@@ -14,9 +14,17 @@
 //   Projector = current_density_projector      (extension) STEP 1 alone on top of the shipped loop
 //   Mover = interpolating_particle_mover       (extension) the commented corner-gather mover, cell.h:905-937
 //
-// The call uploads the universe, steps, and downloads it again, so callers may read and modify
+// By default the call uploads the universe, steps, and downloads it again, so callers may read and modify
 // `universe.cells[...]` / `universe.field[...]` between calls like the reference's tests do.  GPU contexts
 // and the pinned staging buffer are kept between calls (releaseDevices() frees them).
+//
+// RESIDENT mode (opt-in: a `ResidentScope` object, or IPIC3D_RESIDENT=1): the universe stays in HBM between calls.
+// The first simulateSteps call on a universe uploads it; later calls on the SAME universe object find it on the
+// device and start stepping at once; nothing is downloaded until somebody asks for it with syncToHost(universe)
+// (the scope's destructor does, so the host universe is current again when the scope ends).  A caller that changes
+// the host universe inside such a scope says so with touch(universe).  This is the shape of the reference's own
+// benchmark protocol (hdr/benchmark.h:38,43: simulateSteps(2) then simulateSteps(5) on the same universe) and of
+// `ipic3d <deck>`, which only needs the per-cell counts afterwards (cellCounts(universe)).
 // GPUs: IPIC3D_GPUS=<n> (default 1) splits the universe into n z-slabs on devices 0..n-1 of this process;
 // IPIC3D_DEVICES=<ordinal,ordinal,...> names the slabs' devices explicitly.
 #pragma once
@@ -113,12 +121,25 @@ namespace ipic3d {
 			std::vector<ipic_ctx*> ctx;
 			void* staging = nullptr;
 			std::uint64_t stagingParticles = 0;
+			// resident mode: which host universe the device state belongs to, whether the host copy is behind it, and what
+			// the last steps changed besides the particles
+			int residentDepth = 0;                   // nesting of ResidentScope objects
+			const void* residentOf = nullptr;
+			bool hostStale = false, fieldsStale = false, currentStale = false, fieldsOnDevice = false;
+
+			bool residentMode() const {
+				if (residentDepth > 0) return true;
+				const char* e = std::getenv("IPIC3D_RESIDENT");
+				return e && std::atoi(e) != 0;
+			}
+			void forget() { residentOf = nullptr; hostStale = fieldsStale = currentStale = fieldsOnDevice = false; }
 
 			void release() {
 				for (ipic_ctx* c : ctx) ipic_destroy(c);
 				ctx.clear();
 				if (staging) ipic_free_pinned(staging);
 				staging = nullptr; stagingParticles = 0;
+				forget();
 			}
 			void prepare(const ipic_props& props, const std::vector<int>& devs) {
 				if (!ctx.empty() && devs == devices && std::memcmp(&props, &abi, sizeof abi) == 0) return;
@@ -195,6 +216,8 @@ namespace ipic3d {
 			detail::writeDensitySnapshot(p, (std::uint64_t)cycle, fileName, [&](std::int64_t x, std::int64_t y, std::int64_t z) { return universe.cells[{ x, y, z }].particles.size(); });
 	}
 
+	namespace detail { inline void downloadUniverse(Session& session, Universe& universe, bool fields, bool current); }
+
 	// frees the GPU contexts and pinned memory kept between simulateSteps calls
 	inline void releaseDevices() { detail::Session::instance().release(); }
 
@@ -228,10 +251,15 @@ namespace ipic3d {
 		session.prepare(abi, devices);
 		std::vector<ipic_ctx*>& ctx = session.ctx;
 
+		// resident mode: the device already holds this universe (left there by an earlier call) -> no upload
+		const bool resident = session.residentMode();
+		const bool onDevice = resident && session.residentOf == static_cast<const void*>(&universe);
+		if (!onDevice) session.forget();
+
 		// ---- upload: every slab's cells in slab order (x*ny + y)*lz + zl, particles cell-major as AoS records
 		std::vector<std::vector<std::uint64_t>> counts((std::size_t)gpus);
 		std::uint64_t largestSlab = 0;
-		for (int r = 0; r < gpus; ++r) {
+		if (!onDevice) for (int r = 0; r < gpus; ++r) {
 			auto& cnt = counts[(std::size_t)r];
 			cnt.reserve((std::size_t)(nx * ny * lz));
 			std::uint64_t total = 0;
@@ -242,7 +270,7 @@ namespace ipic3d {
 			largestSlab = std::max(largestSlab, total);
 		}
 		// room for migration into a slab while it is on the device
-		session.reserveStaging(largestSlab + largestSlab / 4 + 65536);
+		if (!onDevice) session.reserveStaging(largestSlab + largestSlab / 4 + 65536);
 		struct { void* p; } staging{ session.staging };
 		// slab cell c = (x*ny + y)*lz + zl  ->  the universe's cell
 		const auto cellOf = [&](int r, std::size_t c) -> Cell& {
@@ -250,7 +278,14 @@ namespace ipic3d {
 			return universe.cells[{ xy / ny, xy % ny, r * lz + zl }];
 		};
 		std::vector<std::uint64_t> offset;
-		for (int r = 0; r < gpus; ++r) {
+		const bool needFields = usesFields || writesCurrent || debugOutput;
+		if (onDevice && needFields && !session.fieldsOnDevice)
+			for (int r = 0; r < gpus; ++r)
+				detail::check(ipic_upload_fields(ctx[(std::size_t)r], reinterpret_cast<const double*>(universe.field.data()),
+				                                 reinterpret_cast<const double*>(universe.bcfield.data()),
+				                                 reinterpret_cast<const double*>(universe.currentDensity.data())), "ipic_upload_fields");
+		if (needFields) session.fieldsOnDevice = true;
+		if (!onDevice) for (int r = 0; r < gpus; ++r) {
 			const auto& cnt = counts[(std::size_t)r];
 			offset.assign(cnt.size() + 1, 0);
 			for (std::size_t c = 0; c < cnt.size(); ++c) offset[c + 1] = offset[c] + cnt[c];
@@ -305,29 +340,126 @@ namespace ipic3d {
 			done = next;
 		}
 
-		// ---- download
-		for (int r = 0; r < gpus; ++r) {
-			auto& cnt = counts[(std::size_t)r];
-			std::uint64_t total = 0;
-			detail::check(ipic_total_particles(ctx[(std::size_t)r], &total), "ipic_total_particles");
-			session.reserveStaging(total);
-			staging.p = session.staging;
-			detail::check(ipic_download_cells(ctx[(std::size_t)r], cnt.data(), static_cast<double*>(staging.p), session.stagingParticles), "ipic_download_cells");
-			offset.assign(cnt.size() + 1, 0);
-			for (std::size_t c = 0; c < cnt.size(); ++c) offset[c + 1] = offset[c] + cnt[c];
-			detail::parallelFor(cnt.size(), [&](std::size_t c) {
-				auto& ps = cellOf(r, c).particles;
-				ps.resize((std::size_t)cnt[c]);
-				if (cnt[c]) std::memcpy(ps.data(), static_cast<const char*>(staging.p) + offset[c] * sizeof(Particle), (std::size_t)cnt[c] * sizeof(Particle));
-			});
+		if (resident) {
+			// the universe stays in HBM; the host copy is brought up to date by syncToHost (ResidentScope's destructor)
+			session.residentOf = &universe;
+			session.hostStale = true;
+			session.fieldsStale = session.fieldsStale || writesFields;
+			session.currentStale = session.currentStale || writesCurrent;
+			const auto endAll = clock::now();
+			return { seconds(endFirst - start), seconds(endAll - endFirst) };
 		}
-		if (writesFields || writesCurrent)     // the grids are replicated on every slab: rank 0 has them all
-			detail::check(ipic_download_fields(ctx[0], writesFields ? reinterpret_cast<double*>(universe.field.data()) : nullptr,
-			                                   writesFields ? reinterpret_cast<double*>(universe.bcfield.data()) : nullptr,
-			                                   writesCurrent ? reinterpret_cast<double*>(universe.currentDensity.data()) : nullptr), "ipic_download_fields");
+		detail::downloadUniverse(session, universe, writesFields, writesCurrent);
 		const auto endAll = clock::now();
 		return { seconds(endFirst - start), seconds(endAll - endFirst) };
 	}
+
+	namespace detail {
+		// device -> host: every slab's particles back into the per-cell vectors, and the grids the steps changed
+		inline void downloadUniverse(Session& session, Universe& universe, bool fields, bool current) {
+			const UniverseProperties& props = universe.properties;
+			const std::int64_t nx = props.size.x, ny = props.size.y, nz = props.size.z;
+			(void)nx;
+			std::vector<ipic_ctx*>& ctx = session.ctx;
+			const int gpus = (int)ctx.size();
+			const std::int64_t lz = nz / gpus;
+			const auto cellOf = [&](int r, std::size_t c) -> Cell& {
+				const std::int64_t xy = (std::int64_t)c / lz, zl = (std::int64_t)c % lz;
+				return universe.cells[{ xy / ny, xy % ny, r * lz + zl }];
+			};
+			std::vector<std::uint64_t> cnt, offset;
+			struct { void* p; } staging{ session.staging };
+			for (int r = 0; r < gpus; ++r) {
+				cnt.assign((std::size_t)(props.size.x * ny * lz), 0);
+				std::uint64_t total = 0;
+				check(ipic_total_particles(ctx[(std::size_t)r], &total), "ipic_total_particles");
+				session.reserveStaging(total);
+				staging.p = session.staging;
+				check(ipic_download_cells(ctx[(std::size_t)r], cnt.data(), static_cast<double*>(staging.p), session.stagingParticles), "ipic_download_cells");
+				offset.assign(cnt.size() + 1, 0);
+				for (std::size_t c = 0; c < cnt.size(); ++c) offset[c + 1] = offset[c] + cnt[c];
+				parallelFor(cnt.size(), [&](std::size_t c) {
+					auto& ps = cellOf(r, c).particles;
+					ps.resize((std::size_t)cnt[c]);
+					if (cnt[c]) std::memcpy(ps.data(), static_cast<const char*>(staging.p) + offset[c] * sizeof(Particle), (std::size_t)cnt[c] * sizeof(Particle));
+				});
+			}
+			if (fields || current)     // the grids are replicated on every slab: rank 0 has them all
+				check(ipic_download_fields(ctx[0], fields ? reinterpret_cast<double*>(universe.field.data()) : nullptr,
+				                           fields ? reinterpret_cast<double*>(universe.bcfield.data()) : nullptr,
+				                           current ? reinterpret_cast<double*>(universe.currentDensity.data()) : nullptr), "ipic_download_fields");
+		}
+	}
+
+	// ---- resident mode (see the header comment) -----------------------------------------------------------------
+
+	// brings the host universe up to date with the device copy left by simulateSteps in resident mode
+	inline void syncToHost(Universe& universe) {
+		detail::Session& session = detail::Session::instance();
+		if (session.residentOf != static_cast<const void*>(&universe) || !session.hostStale) return;
+		detail::downloadUniverse(session, universe, session.fieldsStale, session.currentStale);
+		session.hostStale = session.fieldsStale = session.currentStale = false;
+	}
+
+	// the caller changed the host universe: the device copy (if any) is dropped, the next call uploads again
+	inline void touch(Universe& universe) {
+		detail::Session& session = detail::Session::instance();
+		if (session.residentOf != static_cast<const void*>(&universe)) return;
+		if (session.hostStale) syncToHost(universe);      // nothing the device computed is lost
+		session.forget();
+	}
+
+	// Per-cell particle counts of a universe wherever it currently lives (x-major, the order of the `.out` file): from the
+	// device when the host copy is stale -- 8 bytes per cell instead of 64 bytes per particle across PCIe.
+	inline std::vector<std::uint64_t> cellCounts(const Universe& universe) {
+		const UniverseProperties& p = universe.properties;
+		std::vector<std::uint64_t> out((std::size_t)(p.size.x * p.size.y * p.size.z));
+		detail::Session& session = detail::Session::instance();
+		if (session.residentOf == static_cast<const void*>(&universe) && session.hostStale) {
+			const int gpus = (int)session.ctx.size();
+			const std::int64_t lz = p.size.z / gpus;
+			std::vector<std::uint64_t> slab((std::size_t)(p.size.x * p.size.y * lz));
+			for (int r = 0; r < gpus; ++r) {
+				detail::check(ipic_cell_counts(session.ctx[(std::size_t)r], slab.data()), "ipic_cell_counts");
+				for (std::size_t c = 0; c < slab.size(); ++c) out[(c / (std::size_t)lz) * (std::size_t)p.size.z + (std::size_t)(r * lz) + c % (std::size_t)lz] = slab[c];
+			}
+		} else {
+			for (std::size_t i = 0; i < out.size(); ++i) out[i] = universe.cells.data()[i].particles.size();
+		}
+		return out;
+	}
+
+	// "<base>.out" of a universe wherever it lives (reference writer: hdr/cell.h:1360-1388, same text)
+	inline void outputNumberOfParticlesPerCell(const Universe& universe, const std::string& outputFilename) {
+		const UniverseProperties& p = universe.properties;
+		const std::vector<std::uint64_t> counts = cellCounts(universe);
+		std::ofstream out(outputFilename);
+		out << p.size << "\n";
+		std::uint64_t total = 0;
+		std::size_t i = 0;
+		for (std::int64_t x = 0; x < p.size.x; ++x) for (std::int64_t y = 0; y < p.size.y; ++y) for (std::int64_t z = 0; z < p.size.z; ++z, ++i) {
+			out << x << "," << y << "," << z << ":" << counts[i] << "\n";
+			total += counts[i];
+		}
+		out << "\nTotal: " << total << "\n";
+	}
+
+	// While an object of this type lives, simulateSteps keeps universes in HBM between calls; at the end of the scope the
+	// host copy of `universe` is brought up to date (unless dismissed: the caller only wanted counts / diagnostics).
+	class ResidentScope {
+		Universe& universe;
+		bool sync = true;
+	public:
+		explicit ResidentScope(Universe& u) : universe(u) { detail::Session::instance().residentDepth++; }
+		ResidentScope(const ResidentScope&) = delete;
+		ResidentScope& operator=(const ResidentScope&) = delete;
+		void dismiss() { sync = false; }
+		~ResidentScope() {
+			detail::Session& session = detail::Session::instance();
+			if (sync) syncToHost(universe);
+			if (--session.residentDepth == 0 && session.residentOf == static_cast<const void*>(&universe)) session.forget();
+		}
+	};
 
 	template<
 		typename ParticleToFieldProjector = detail::default_particle_to_field_projector,

@@ -135,6 +135,67 @@ IPIC_API void* ipic_mirror_create_benchmark(char kind, uint64_t numParticles, ip
 	return h;
 }
 
+// ---- an input deck piecewise: phase 1 of initCells once, then the particles of any z-slab straight into caller memory ----
+// (what a rank of a multi-GPU run needs: its own planes of `ipic3d <deck>`'s universe, never the whole of it)
+
+struct DeckHandle {
+	ipic3d::EarthDeck deck;
+	std::vector<std::uint64_t> population;       // every cell of the universe, z-fastest flatten
+	explicit DeckHandle(const char* path) : deck(std::string(path)) {}
+};
+
+IPIC_API void* ipic_host_deck_open(const char* path, ipic_props* props, uint64_t* ncycles, int64_t* numParticles) {
+	std::ostringstream quiet;
+	auto* old = std::cout.rdbuf(quiet.rdbuf());
+	auto* h = new DeckHandle(path);
+	h->population = h->deck.cellPopulations();
+	std::cout.rdbuf(old);
+	if (props) *props = h->deck.properties.toAbi();
+	if (ncycles) *ncycles = h->deck.params.ncycles;
+	if (numParticles) *numParticles = h->deck.numParticles;
+	return h;
+}
+
+IPIC_API void ipic_host_deck_close(void* handle) { delete static_cast<DeckHandle*>(handle); }
+
+// populations of the z-planes [zBegin, zBegin + zCount) in slab order (x*ny + y)*zCount + zl
+IPIC_API int ipic_host_deck_counts(void* handle, int zBegin, int zCount, uint64_t* counts) {
+	const DeckHandle* h = static_cast<DeckHandle*>(handle);
+	const auto size = h->deck.properties.size;
+	if (!counts || zBegin < 0 || zCount < 0 || zBegin + zCount > size.z) return IPIC_ERR_ARG;
+	for (std::int64_t xy = 0; xy < size.x * size.y; ++xy) for (int zl = 0; zl < zCount; ++zl)
+		*counts++ = h->population[(std::size_t)(xy * size.z + zBegin + zl)];
+	return IPIC_OK;
+}
+
+// particles of the same cells, AoS of 8 doubles, cell-major in slab order; `threads` <= 0 = all cores
+IPIC_API int ipic_host_deck_particles(void* handle, int zBegin, int zCount, double* aos, int threads) {
+	const DeckHandle* h = static_cast<DeckHandle*>(handle);
+	const auto size = h->deck.properties.size;
+	if (!aos || zBegin < 0 || zCount < 0 || zBegin + zCount > size.z) return IPIC_ERR_ARG;
+	static_assert(sizeof(ipic3d::Particle) == 64, "Particle is the 8-double record of the C ABI");
+	const std::int64_t slabCells = size.x * size.y * zCount;
+	std::vector<std::uint64_t> start((std::size_t)slabCells + 1, 0);
+	for (std::int64_t c = 0; c < slabCells; ++c) start[(std::size_t)c + 1] = start[(std::size_t)c] + h->population[(std::size_t)((c / zCount) * size.z + zBegin + c % zCount)];
+	if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+	if (threads <= 0) threads = 1;
+	std::atomic<std::int64_t> next(0);
+	auto work = [&]() {
+		for (;;) {
+			const std::int64_t c = next.fetch_add(1);
+			if (c >= slabCells) return;
+			const std::int64_t xy = c / zCount;
+			const ipic3d::coordinate_type pos{ xy / size.y, xy % size.y, zBegin + c % zCount };
+			h->deck.populateCell(pos, start[(std::size_t)c + 1] - start[(std::size_t)c], reinterpret_cast<ipic3d::Particle*>(aos) + start[(std::size_t)c]);
+		}
+	};
+	std::vector<std::thread> pool;
+	for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+	work();
+	for (auto& t : pool) t.join();
+	return IPIC_OK;
+}
+
 IPIC_API void ipic_mirror_destroy(void* handle) { delete static_cast<MirrorUniverse*>(handle); }
 
 IPIC_API uint64_t ipic_mirror_total(void* handle) { return ipic3d::countParticlesInDomain(static_cast<MirrorUniverse*>(handle)->universe); }

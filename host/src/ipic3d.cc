@@ -31,6 +31,11 @@ namespace {
 		std::cout << "Running simulation..." << std::endl;
 		const std::uint64_t cycles = deck.params.ncycles;
 		const int n = deck.numParticles;
+		// the run only reports per-cell counts afterwards: leave the particles in HBM (IPIC3D_RESIDENT=0: download them all)
+		const char* residentEnv = std::getenv("IPIC3D_RESIDENT");
+		const bool resident = !(residentEnv && std::atoi(residentEnv) == 0);
+		struct OptionalScope { ResidentScope* s; ~OptionalScope() { delete s; } } scope{ resident ? new ResidentScope(universe) : nullptr };
+		if (resident) scope.s->dismiss();
 		const DurationMeasurement t = simulateSteps(cycles, universe);
 
 		std::cout << "Simulation measurements: " << n << " initial particles, first step " << t.firstStep << " seconds, " << (n / t.firstStep)
@@ -38,7 +43,7 @@ namespace {
 		          << "Throughput: " << (cycles * double(n)) / t.remainingSteps << " particles/s \n";
 
 		std::cout << "Simulation finished successfully, producing output data..." << std::endl;
-		outputNumberOfParticlesPerCell(universe.cells, baseName + ".out");
+		outputNumberOfParticlesPerCell(universe, baseName + ".out");       // from the device's per-cell counters when the universe lives there
 		return EXIT_SUCCESS;
 	}
 }

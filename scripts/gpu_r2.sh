@@ -32,6 +32,11 @@ ncuall)
   ncu --set full --clock-control none --import-source on -k regex:'k_move<' -s 4 -c 1 -f -o /tmp/prof_k_move_interp python scripts/probe_kernels.py > /tmp/ncu_k_move_interp.log 2>&1
   python scripts/ncu_summary.py /tmp/prof_k_move_interp.ncu-rep --mix --top 8 > gpurun_out/${TAG}_k_move_interp_summary.txt 2>&1
   ;;
+dipvar)
+  for v in "" "IPIC_WS_DIPOLE=1" "IPIC_LIB=allscale_ipic3d_b200/lib/var_dep6.so" "IPIC_LIB=allscale_ipic3d_b200/lib/var_dep4.so" "IPIC_STAGES=2" "IPIC_STAGES=3"; do
+    echo -n "dipole [$v] : "; env $v python bench.py --workload dipole --steps 20 --warmup 12 $Q 2>/dev/null | python scripts/short.py | cut -d'|' -f1-4
+  done ;;
+medium) python bench.py --workload medium --steps 20 --warmup 5 > gpurun_out/medium_$TAG.json 2> gpurun_out/medium_$TAG.err; tail -3 gpurun_out/medium_$TAG.err; python scripts/short.py < gpurun_out/medium_$TAG.json ;;
 sanitize)
   compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/sanitize_case.py > gpurun_out/memcheck_$TAG.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/memcheck_$TAG.log
   compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/sanitize_case.py > gpurun_out/racecheck_$TAG.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/racecheck_$TAG.log

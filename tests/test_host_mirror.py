@@ -59,6 +59,24 @@ def test_inp_universe_bit_identical(mirror, deck):
     assert_same_universe(mirror_state(mirror, h, props), ref)
 
 
+@pytest.mark.parametrize("deck,world", [("test.inp", 1), ("test.inp", 2), ("test.inp", 8), ("tiny.inp", 4)])
+def test_deck_generated_slab_by_slab(deck, world):
+    """capi.Deck: phase 1 of initCells once, then every z-slab on its own (what a rank of a multi-GPU run does) --
+    put together, the slabs are the reference's universe bit for bit."""
+    from allscale_ipic3d_b200 import capi
+    path = os.path.join(GOLDEN_INPUTS, deck)
+    ref = Ref.from_inp(path)
+    want_counts, want_aos = ref.counts(), ref.particles()
+    with capi.Deck(path) as d:
+        assert bytes(d.props) == bytes(ref.props)
+        assert (d.ncycles, d.num_particles) == (ref.ncycles, ref.num_particles)
+        nz = int(d.props.size[2]); nxy = int(d.props.size[0] * d.props.size[1])
+        for rank in range(world):
+            counts, aos = d.slab(rank, world)
+            wc, wa = capi.slab_of(want_counts, want_aos, nxy, nz, rank, world)
+            assert np.array_equal(counts, wc) and bits_equal(aos, wa), "slab %d of %d" % (rank, world)
+
+
 @pytest.mark.parametrize("kind,n", [("U", 300000), ("C", 200000), ("E", 100000), ("B", 100000)])
 def test_benchmark_universes_bit_identical(mirror, kind, n):
     """`ipic3d :U:N`, `:C:N`, `:E:N`, `:B:N` (normal / spherical / beam generators, 32^3 grid)."""
