@@ -29,7 +29,7 @@ ncuall)
     ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o /tmp/prof_${k} python scripts/probe_kernels.py > /tmp/ncu_${k}.log 2>&1
     python scripts/ncu_summary.py /tmp/prof_${k}.ncu-rep --mix --top 8 > gpurun_out/${TAG}_${k}_summary.txt 2>&1; rm -f /tmp/prof_${k}.ncu-rep
   done
-  ncu --set full --clock-control none --import-source on -k regex:'k_move<' -s 4 -c 1 -f -o /tmp/prof_k_move_interp python scripts/probe_kernels.py > /tmp/ncu_k_move_interp.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:k_move -s 5 -c 1 -f -o /tmp/prof_k_move_interp python scripts/probe_kernels.py > /tmp/ncu_k_move_interp.log 2>&1
   python scripts/ncu_summary.py /tmp/prof_k_move_interp.ncu-rep --mix --top 8 > gpurun_out/${TAG}_k_move_interp_summary.txt 2>&1
   ;;
 dipvar)

@@ -27,6 +27,16 @@ with ipic.Context(props) as c:
     c.set_uniform_species(True)
     c.upload_cells(counts, aos)                             # k_check_species, k_scatter_aos
 
+# a cell-segment overflow: re-layout (k_copy_heads) and redo of the import
+with ipic.Context(props) as c:
+    conv = aos.copy()
+    conv[:, 3:6] = 0.0
+    conv[:, 3] = np.where(conv[:, 0] < 160.0, 60.0, -60.0)     # everybody converges on the two middle x-planes
+    c.set_headroom(0.05, 32)
+    c.upload_cells(counts, conv)
+    c.step(12, 0)
+    print("relayouts", c.relayout_count())
+
 os.environ["IPIC_CHUNKED"] = "1"
 with ipic.Context(props) as c:
     c.upload_cells(counts, aos)
