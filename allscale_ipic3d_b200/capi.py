@@ -22,7 +22,7 @@ API_SYMBOLS = [
     "ipic_step_async", "ipic_sync", "ipic_count_misplaced", "ipic_profile_reset", "ipic_profile_get", "ipic_selftest",
     "ipic_set_exchange_capacity", "ipic_group_create", "ipic_group_step", "ipic_relayout_count",
     "ipic_alloc_pinned", "ipic_free_pinned", "ipic_set_uniform_species", "ipic_particle_fields", "ipic_profile_phases",
-    "ipic_diagnostics", "ipic_group_diagnostics", "ipic_trace", "ipic_generate_uniform",
+    "ipic_diagnostics", "ipic_group_diagnostics", "ipic_trace", "ipic_generate_uniform", "ipic_generate_normal_speed",
 ]
 
 
@@ -234,6 +234,15 @@ class Context:
     def generate_uniform(self, num_particles):
         """The reference's `:U:N` universe (this context's cells) generated on the device, bit-identical to initCells."""
         self._ck(self.lib.ipic_generate_uniform(self.h, C.c_uint64(num_particles)))
+
+    def generate_normal_speed(self, counts, mean, stddev, q, qom):
+        """An `.inp` deck's universe (this context's cells) generated on the device: phase 2 of initCells, bit-identical to the host's."""
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        if counts.size != self.owned_cells:
+            raise ValueError("one count per owned cell")
+        m = (C.c_double * 3)(*mean)
+        s = (C.c_double * 3)(*stddev)
+        self._ck(self.lib.ipic_generate_normal_speed(self.h, _up(counts), m, s, C.c_double(q), C.c_double(qom)))
 
     def diagnostics(self):
         """(total momentum, E energy, B energy, total kinetic energy): the columns of ConservedQuantities.out, reduced on the device."""
@@ -486,6 +495,20 @@ class Deck:
         z_count = int(self.props.size[2]) - z_begin if z_count is None else z_count
         if self.lib.ipic_host_deck_particles(self.h, C.c_int(z_begin), C.c_int(z_count), C.c_void_p(aos_ptr), C.c_int(threads)):
             raise IpicError(-1, "ipic_host_deck_particles: bad arguments")
+
+    def distribution(self):
+        """(mean[3], stddev[3], q, qom) of phase 2: what ipic_generate_normal_speed needs besides the populations."""
+        m, s = (C.c_double * 3)(), (C.c_double * 3)()
+        q, qom = C.c_double(0), C.c_double(0)
+        self.lib.ipic_host_deck_distribution(self.h, m, s, C.byref(q), C.byref(qom))
+        return list(m), list(s), q.value, qom.value
+
+    def generate_on_device(self, ctx, rank=0, world=1):
+        """z-slab `rank` of `world` created in the context's HBM (phase 1 populations from the host, phase 2 on the GPU)."""
+        lz = int(self.props.size[2]) // world
+        counts = self.counts(rank * lz, lz)
+        ctx.generate_normal_speed(counts, *self.distribution())
+        return counts
 
     def slab(self, rank=0, world=1):
         """(counts, particles) of z-slab `rank` of `world` in slab order."""

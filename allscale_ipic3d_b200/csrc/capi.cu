@@ -62,6 +62,9 @@ struct ipic_ctx {
 	int* dStay = nullptr;                          // stayers per cell after the mover (head of segment, other generation)
 	int* dLeave = nullptr;                         // outbox entries per local cell
 	unsigned char* dTag = nullptr;                 // direction tag per slot (outbox entries only)
+	unsigned short* dOrder = nullptr;              // per slot: the movers' direction-sorted index of each cell's outbox (sort_outbox)
+	ZigguratTables* dZiggurat = nullptr;           // tables of the deck generator (ipic_generate_normal_speed), made on first use
+	int* dDirOff = nullptr;                        // per local cell: 28 prefix counts over the direction codes of its outbox (-1: not indexed)
 	// chunked mover (k_move_chunk): chunk table of the current layout, ordered plane 0 | interior planes | last plane
 	bool chunked = false;                          // chosen at upload / re-layout from the populations (IPIC_CHUNKED=0/1 forces)
 	int2* dChunkTable = nullptr;
@@ -70,7 +73,7 @@ struct ipic_ctx {
 	double* dChunkJ = nullptr;
 	int chunkRange[4] = { 0, 0, 0, 0 };            // table offsets: plane 0 = [r0, r1), interior = [r1, r2), last plane = [r2, r3)
 	int64_t chunkCapacity = 0;                     // chunks the device arrays were allocated for
-	int* dStop = nullptr;                          // [0] stop, [1] first failing step, [2] cell overflow seen in this import pass, [3] exchange failure (1 face message full on this rank, 2 unusable message received)
+	int* dStop = nullptr;                          // 8 control words: [0] stop, [1] first failing step, [2] cell overflow seen in this import pass, [3] exchange failure (1 face message full on this rank, 2 unusable message received), [4] an outbox awaits k_sort_outbox
 	bool haveCells = false;
 	int64_t meanPopulation = 0;                    // particles per owned cell at upload (drives the mover's tile shape)
 	double slack = 0.25;                           // head-room per cell as a fraction of its population
@@ -100,6 +103,9 @@ struct ipic_ctx {
 	double phaseMs[4] = { 0, 0, 0, 0 };             // slab steps: [0] movers (span), [1] imports, [2] waiting for the exchange, [3] waiting for J + field phase
 	uint64_t launches = 0;
 	uint64_t relayouts = 0;                        // cell-segment overflows repaired so far
+	// k_sort_outbox follows the movers only while outboxes of more than 32 entries occur: unknown after an upload (assume yes),
+	// then whatever the movers reported (dStop[5], sticky) when the host last looked -- a wrong guess costs speed, never results
+	bool sortLikely = true;
 	// batch enqueued by ipic_step_async and not yet settled: generation at its start, steps, flags
 	uint64_t asyncSteps = 0;
 	int asyncGenAtStart = 0;
@@ -138,14 +144,17 @@ void freeParticleBuffers(ipic_ctx* c) {
 	for (int b = 0; b < 2; b++) { if (c->buf[b].d) cudaFree(c->buf[b].d); c->buf[b].d = nullptr; }
 	if (c->dTag) cudaFree(c->dTag);
 	c->dTag = nullptr;
+	if (c->dOrder) cudaFree(c->dOrder);
+	c->dOrder = nullptr;
 	c->slots = 0;
 	c->slotsNf = 0;
 }
 
-int allocParticleBuffers(ParticleArrays out[2], unsigned char** tag, int64_t slots, int nf) {
+int allocParticleBuffers(ParticleArrays out[2], unsigned char** tag, unsigned short** order, int64_t slots, int nf) {
 	// slots is a multiple of 32: whole AoSoA-32 blocks of 32*nf doubles
 	for (int b = 0; b < 2; b++) CK(cudaMalloc(&out[b].d, (size_t)std::max<int64_t>(slots, 32) * nf * sizeof(double)));
 	CK(cudaMalloc(tag, (size_t)std::max<int64_t>(slots, 1)));
+	CK(cudaMalloc(order, (size_t)std::max<int64_t>(slots, 1) * sizeof(unsigned short)));
 	return IPIC_OK;
 }
 
@@ -295,9 +304,8 @@ FaceMsg faceView(const ipic_ctx* c, char* base, int cap) {
 	const int nxy = c->g.nx * c->g.ny;
 	FaceMsg m;
 	m.offsets = reinterpret_cast<int*>(base);
-	const size_t offP = (size_t)alignUp((int64_t)(nxy + 1) * 4, 128);
+	const size_t offP = (size_t)alignUp((int64_t)(nxy * 9 + 1) * 4, 128);
 	m.particles = reinterpret_cast<double*>(base + offP);
-	m.tags = reinterpret_cast<unsigned char*>(base + offP + (size_t)cap * 64);
 	m.cap = cap;
 	return m;
 }
@@ -325,24 +333,25 @@ int relayoutAfterOverflow(ipic_ctx* c, int outGen, int failedStep) {
 		c->padFloor = std::min<int64_t>(std::max<int64_t>(2 * c->padFloor, mean / 4), 2 * mean + 64);
 	}
 	buildLayout(c, need64, newStart);
-	ParticleArrays nb[2]{}; unsigned char* ntag = nullptr;
+	ParticleArrays nb[2]{}; unsigned char* ntag = nullptr; unsigned short* norder = nullptr;
 	int64_t* dNewStart = nullptr;
 	// until the new storage is swapped in, a failure frees it again
-	struct Fresh { ParticleArrays* nb; unsigned char** tag; int64_t** start; bool armed;
-	               ~Fresh() { if (armed) { cudaFree(nb[0].d); cudaFree(nb[1].d); cudaFree(*tag); cudaFree(*start); } } } fresh{ nb, &ntag, &dNewStart, true };
+	struct Fresh { ParticleArrays* nb; unsigned char** tag; unsigned short** order; int64_t** start; bool armed;
+	               ~Fresh() { if (armed) { cudaFree(nb[0].d); cudaFree(nb[1].d); cudaFree(*tag); cudaFree(*order); cudaFree(*start); } } } fresh{ nb, &ntag, &norder, &dNewStart, true };
 	const int64_t nslots = newStart.back();
-	rc = allocParticleBuffers(nb, &ntag, nslots, c->g.nf);
+	rc = allocParticleBuffers(nb, &ntag, &norder, nslots, c->g.nf);
 	if (rc) return rc;
 	CK(cudaMalloc(&dNewStart, newStart.size() * sizeof(int64_t)));
 	CK(cudaMemcpyAsync(dNewStart, newStart.data(), newStart.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-	CK(cudaMemsetAsync(c->dStop, 0, 4 * sizeof(int), c->stream));
+	CK(cudaMemsetAsync(c->dStop, 0, 4 * sizeof(int), c->stream));      // [4] (sort flag) stays: the failed step's outbox index is in use
 	int big = 0x7fffffff;
 	CK(cudaMemcpyAsync(c->dStop + 1, &big, sizeof(int), cudaMemcpyHostToDevice, c->stream));
 	launch_copy_heads(c->g, c->buf[outGen], c->dCellStart, nb[outGen], dNewStart, c->dStay, c->g.nf, c->g.uq, c->g.uqom, c->stream);
 	ImportArgs ia{};
 	ia.g = c->g; ia.src = c->buf[outGen]; ia.srcStart = c->dCellStart; ia.srcLeave = c->dLeave; ia.tag = c->dTag;
+	ia.order = c->dOrder; ia.dirOff = c->dDirOff;          // the failed step's outbox index, slots of the OLD layout
 	ia.dst = nb[outGen]; ia.dstStart = dNewStart; ia.stay = c->dStay; ia.dstCount = c->dCount;
-	ia.reserveOwnOutbox = 0; ia.stopFlag = c->dStop; ia.stepIndex = failedStep; ia.zBegin = 0; ia.zCount = c->g.lz;
+	ia.reserveOwnOutbox = 0; ia.stopFlag = c->dStop; ia.stepIndex = failedStep; ia.zBegin = 0; ia.zCount = c->g.lz; ia.zStride = 1;
 	setImportSources(c, ia);
 	launch_import(ia, true, c->stream);
 	c->launches += 3;
@@ -353,7 +362,7 @@ int relayoutAfterOverflow(ipic_ctx* c, int outGen, int failedStep) {
 	fresh.armed = false;
 	freeParticleBuffers(c);
 	cudaFree(c->dCellStart);
-	c->buf[0] = nb[0]; c->buf[1] = nb[1]; c->dTag = ntag; c->dCellStart = dNewStart; c->slots = nslots; c->slotsNf = c->g.nf; c->hCellStart = newStart;
+	c->buf[0] = nb[0]; c->buf[1] = nb[1]; c->dTag = ntag; c->dOrder = norder; c->dCellStart = dNewStart; c->slots = nslots; c->slotsNf = c->g.nf; c->hCellStart = newStart;
 	if (stop[0]) return fail(IPIC_ERR_INTERNAL, "relayout did not resolve the overflow of step %d", failedStep);
 	return buildChunkTable(c, *std::max_element(need64.begin(), need64.end()));
 }
@@ -363,8 +372,8 @@ int relayoutAfterOverflow(ipic_ctx* c, int outGen, int failedStep) {
 int convertToFullLayout(ipic_ctx* c) {
 	if (c->g.nf == kFields) return IPIC_OK;
 	CK(cudaSetDevice(c->device));
-	ParticleArrays nb[2]{}; unsigned char* ntag = nullptr;
-	int rc = allocParticleBuffers(nb, &ntag, c->slots, kFields);
+	ParticleArrays nb[2]{}; unsigned char* ntag = nullptr; unsigned short* norder = nullptr;
+	int rc = allocParticleBuffers(nb, &ntag, &norder, c->slots, kFields);
 	if (rc) return rc;
 	Geometry wide = c->g;
 	wide.nf = kFields;
@@ -373,7 +382,7 @@ int convertToFullLayout(ipic_ctx* c) {
 	CK(cudaStreamSynchronize(c->stream));
 	const int64_t slots = c->slots;
 	freeParticleBuffers(c);
-	c->buf[0] = nb[0]; c->buf[1] = nb[1]; c->dTag = ntag; c->slots = slots; c->slotsNf = kFields;
+	c->buf[0] = nb[0]; c->buf[1] = nb[1]; c->dTag = ntag; c->dOrder = norder; c->slots = slots; c->slotsNf = kFields;
 	c->g = wide;
 	return IPIC_OK;
 }
@@ -432,8 +441,10 @@ int ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, 
 	CK(cudaMemset(c->dCount, 0, (size_t)g.ncellsLocal * sizeof(int)));
 	CK(cudaMemset(c->dStay, 0, (size_t)g.ncellsLocal * sizeof(int)));
 	CK(cudaMemset(c->dLeave, 0, (size_t)g.ncellsLocal * sizeof(int)));
-	CK(cudaMalloc(&c->dStop, 4 * sizeof(int)));
-	int stop[4] = { 0, 0x7fffffff, 0, 0 };
+	CK(cudaMalloc(&c->dDirOff, (size_t)std::max(1, g.ncellsLocal) * 28 * sizeof(int)));
+	CK(cudaMemset(c->dDirOff, 0, (size_t)std::max(1, g.ncellsLocal) * 28 * sizeof(int)));
+	CK(cudaMalloc(&c->dStop, 8 * sizeof(int)));
+	int stop[8] = { 0, 0x7fffffff, 0, 0, 0, 0, 0, 0 };
 	CK(cudaMemcpy(c->dStop, stop, sizeof stop, cudaMemcpyHostToDevice));
 	c->nField = (int64_t)(g.nx + 3) * (g.ny + 3) * (g.nz + 3);
 	c->nBc = (int64_t)(g.nx + 2) * (g.ny + 2) * (g.nz + 2);
@@ -450,18 +461,21 @@ int ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, 
 	CK(cudaMemset(c->dCellJ, 0, (size_t)g.nx * g.ny * g.nz * 24 * sizeof(double)));
 	CK(cudaMalloc(&c->dAosStart, ((size_t)ownedCells(c) + 1) * sizeof(int64_t)));
 	if (nranks > 1) {
-		CK(cudaStreamCreateWithFlags(&c->commStream, cudaStreamNonBlocking));
 		int prLow = 0, prHigh = 0;
 		CK(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+		// both side streams run at high priority: the block scheduler takes their (few) CTAs -- the boundary planes' movers, the
+		// face packing, NCCL's send / receive kernels -- ahead of the tens of thousands of interior-mover CTAs queued on the main stream
+		CK(cudaStreamCreateWithPriority(&c->commStream, cudaStreamNonBlocking, prHigh));
 		CK(cudaStreamCreateWithPriority(&c->bStream, cudaStreamNonBlocking, prHigh));
 		for (cudaEvent_t* e : { &c->evPacked, &c->evRecv, &c->evMoved, &c->evJ, &c->evMainReady }) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 		CK(cudaMalloc(&c->dTotals, 4 * sizeof(int)));
 		CK(cudaMemset(c->dTotals, 0, 4 * sizeof(int)));
 		CK(cudaMallocHost(&c->hTotals, 4 * sizeof(int)));
 		std::memset(c->hTotals, 0, 4 * sizeof(int));
-		CK(cudaMalloc(&c->dFaceCnt, (size_t)2 * g.nx * g.ny * sizeof(int)));
+		CK(cudaMalloc(&c->dFaceCnt, (size_t)2 * g.nx * g.ny * 9 * sizeof(int)));
 		CK(cudaMalloc(&c->dNegotiate, (size_t)nranks * 4 * sizeof(int64_t)));
-		CK(cudaMallocHost(&c->hStop, 4 * sizeof(int)));
+		CK(cudaMallocHost(&c->hStop, 8 * sizeof(int)));
+		std::memset(c->hStop, 0, 8 * sizeof(int));
 		CK(cudaEventCreateWithFlags(&c->evStepDone, cudaEventDisableTiming));
 	}
 	guard.c = nullptr;
@@ -493,10 +507,10 @@ int ipic_destroy(ipic_ctx* c) {
 	if (c->commStream) cudaStreamDestroy(c->commStream);
 	if (c->bStream) cudaStreamDestroy(c->bStream);
 	freeParticleBuffers(c);
-	cudaFree(c->dCellStart); cudaFree(c->dCount); cudaFree(c->dStay); cudaFree(c->dLeave); cudaFree(c->dStop);
+	cudaFree(c->dCellStart); cudaFree(c->dCount); cudaFree(c->dStay); cudaFree(c->dLeave); cudaFree(c->dStop); cudaFree(c->dDirOff);
 	cudaFree(c->dChunkTable); cudaFree(c->dChunkStatus); cudaFree(c->dChunkTicket); cudaFree(c->dChunkJ);
 	cudaFree(c->dEB); cudaFree(c->dBext); cudaFree(c->dBc); cudaFree(c->dJ); cudaFree(c->dCellJ);
-	cudaFree(c->dStage); cudaFree(c->dAosStart);
+	cudaFree(c->dStage); cudaFree(c->dAosStart); cudaFree(c->dZiggurat);
 	for (auto e : c->events) cudaEventDestroy(e);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -551,7 +565,7 @@ int establishLayout(ipic_ctx* c, const std::vector<int64_t>& need, int nf, doubl
 	buildLayout(c, need, start);
 	if (start.back() > c->slots || start.back() < c->slots / 2 || c->slotsNf != nf) {
 		freeParticleBuffers(c);
-		int rc = allocParticleBuffers(c->buf, &c->dTag, start.back(), nf);
+		int rc = allocParticleBuffers(c->buf, &c->dTag, &c->dOrder, start.back(), nf);
 		if (rc) return rc;
 		c->slots = start.back();
 		c->slotsNf = nf;
@@ -564,6 +578,7 @@ int establishLayout(ipic_ctx* c, const std::vector<int64_t>& need, int nf, doubl
 	CK(cudaMemsetAsync(c->dLeave, 0, (size_t)c->g.ncellsLocal * sizeof(int), c->stream));
 	CK(cudaStreamSynchronize(c->stream));     // the host vectors above go out of scope
 	c->haveCells = true;
+	c->sortLikely = true;
 	c->emptyUpload = total == 0;
 	c->meanPopulation = total / std::max(1, nOwned);
 	if (c->nranks > 1) {
@@ -636,6 +651,53 @@ int ipic_generate_uniform(ipic_ctx* c, uint64_t numParticles) {
 	if (rc) return rc;
 	launch_init_uniform(c->g, c->buf[c->cur], c->dCellStart, c->dCount, c->stream);
 	c->launches++;
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaGetLastError());
+	return IPIC_OK;
+}
+
+// the reference's zigset (hdr/ziggurat_normal_distribution.h:107-125) with the host's libm, like the reference itself
+static void zigguratTables(ZigguratTables& t) {
+	const double m1 = 2147483648.0;
+	double dn = 3.442619855899, tn = dn;
+	const double vn = 9.91256303526217e-3;
+	const double q = vn / std::exp(-.5 * dn * dn);
+	t.kn[0] = (unsigned long long)((dn / q) * m1);
+	t.kn[1] = 0;
+	t.wn[0] = (float)(q / m1);
+	t.wn[127] = (float)(dn / m1);
+	t.fn[0] = 1.;
+	t.fn[127] = (float)std::exp(-.5 * dn * dn);
+	for (int i = 126; i >= 1; --i) {
+		dn = std::sqrt(-2. * std::log(vn / dn + std::exp(-.5 * dn * dn)));
+		t.kn[i + 1] = (unsigned long long)((dn / tn) * m1);
+		tn = dn;
+		t.fn[i] = (float)std::exp(-.5 * dn * dn);
+		t.wn[i] = (float)(dn / m1);
+	}
+}
+
+int ipic_generate_normal_speed(ipic_ctx* c, const uint64_t* counts, const double* mean3, const double* stddev3, double q, double qom) {
+	if (!c || !counts || !mean3 || !stddev3) return fail(IPIC_ERR_ARG, "null argument");
+	CK(cudaSetDevice(c->device));
+	{ int rcA = settleAsync(c); if (rcA) return rcA; }
+	const int nOwned = ownedCells(c);
+	std::vector<int64_t> need((size_t)nOwned);
+	for (int i = 0; i < nOwned; i++) {
+		if (counts[i] > 0x3fffffffu) return fail(IPIC_ERR_ARG, "cell %d holds %llu particles (limit 2^30 per cell)", i, (unsigned long long)counts[i]);
+		need[(size_t)i] = (int64_t)counts[i];
+	}
+	const bool oneSpecies = c->allowUniformSpecies;
+	int rc = establishLayout(c, need, oneSpecies ? 6 : kFields, q, qom);
+	if (rc) return rc;
+	if (!c->dZiggurat) {
+		ZigguratTables t;
+		zigguratTables(t);
+		CK(cudaMalloc(&c->dZiggurat, sizeof t));
+		CK(cudaMemcpy(c->dZiggurat, &t, sizeof t, cudaMemcpyHostToDevice));
+	}
+	launch_init_deck(c->g, c->buf[c->cur], c->dCellStart, c->dCount, c->dZiggurat, mean3, stddev3, c->stream);
+	c->launches += 2;
 	CK(cudaStreamSynchronize(c->stream));
 	CK(cudaGetLastError());
 	return IPIC_OK;
@@ -740,17 +802,17 @@ struct StepFlags {
 	}
 };
 
-MoveArgs moveArgs(ipic_ctx* c, const StepFlags& f, int zBegin, int zCount) {
+MoveArgs moveArgs(ipic_ctx* c, const StepFlags& f, int zBegin, int zCount, int zStride = 1) {
 	const int in = c->cur, out = c->cur ^ 1;
 	MoveArgs ma{};
 	ma.g = c->g; ma.in = c->buf[in]; ma.out = c->buf[out]; ma.cellStart = c->dCellStart;
-	ma.countIn = c->dCount; ma.countOut = c->dStay; ma.nLeave = c->dLeave; ma.tag = c->dTag;
+	ma.countIn = c->dCount; ma.countOut = c->dStay; ma.nLeave = c->dLeave; ma.tag = c->dTag; ma.order = c->dOrder; ma.dirOff = c->dDirOff;
 	ma.fieldEB = c->dEB; ma.cellJ = c->dCellJ; ma.stopFlag = c->dStop;
-	ma.zBegin = zBegin; ma.zCount = zCount;
-	ma.interpolate = f.interp; ma.migrate = f.migrate; ma.push = true; ma.deposit = f.fuseDeposit;
+	ma.zBegin = zBegin; ma.zCount = zCount; ma.zStride = zStride;
+	ma.interpolate = f.interp; ma.migrate = f.migrate; ma.push = true; ma.deposit = f.fuseDeposit; ma.sortPass = c->sortLikely;
 	pickTileShape(c, ma.deposit, !f.interp, ma.stages);
 	ma.chunked = false;
-	if (c->chunked) {
+	if (c->chunked && zStride == 1) {
 		const int lz = c->g.lz;
 		int grp = -1;
 		if (zBegin == 0 && zCount == lz) grp = 3;
@@ -778,17 +840,17 @@ void depositPass(ipic_ctx* c, const StepFlags& f, int zBegin, int zCount) {
 	MoveArgs da = moveArgs(c, f, zBegin, zCount);
 	da.push = false; da.deposit = true; da.interpolate = false;
 	pickTileShape(c, true, false, da.stages);
-	launch_move(da, c->stream);
-	c->launches++;
+	c->launches += launch_move(da, c->stream);
 }
 
-void importPlanes(ipic_ctx* c, int stepIndex, int zBegin, int zCount, bool commit) {
+void importPlanes(ipic_ctx* c, int stepIndex, int zBegin, int zCount, bool commit, int zStride = 1) {
 	if (zCount <= 0) return;
 	const int out = c->cur ^ 1;
 	ImportArgs ia{};
 	ia.g = c->g; ia.src = c->buf[out]; ia.srcStart = c->dCellStart; ia.srcLeave = c->dLeave; ia.tag = c->dTag;
+	ia.order = c->dOrder; ia.dirOff = c->dDirOff;
 	ia.dst = c->buf[out]; ia.dstStart = c->dCellStart; ia.stay = c->dStay; ia.dstCount = c->dCount;
-	ia.reserveOwnOutbox = 1; ia.stopFlag = c->dStop; ia.stepIndex = stepIndex; ia.zBegin = zBegin; ia.zCount = zCount;
+	ia.reserveOwnOutbox = 1; ia.stopFlag = c->dStop; ia.stepIndex = stepIndex; ia.zBegin = zBegin; ia.zCount = zCount; ia.zStride = zStride;
 	setImportSources(c, ia);
 	launch_import(ia, commit, c->stream);
 	c->launches += commit ? 2 : 1;
@@ -818,8 +880,7 @@ int enqueueStepSingle(ipic_ctx* c, const StepFlags& f, int stepIndex) {
 	if (!f.fuseDeposit) fieldPhase(c, f);
 	{
 		ProfSpan span(c, 0);
-		launch_move(moveArgs(c, f, 0, c->g.lz), c->stream);
-		c->launches++;
+		c->launches += launch_move(moveArgs(c, f, 0, c->g.lz), c->stream);
 	}
 	if (f.fuseDeposit) {
 		launch_gather_current(c->g, c->dCellJ, c->dJ, c->dStop, c->stream);
@@ -862,7 +923,7 @@ enum SlabPhase { PH_PRE_DEPOSIT, PH_PRE_GATHER_J, PH_BOUNDARY, PH_INTERIOR, PH_S
 
 size_t faceBytes(const ipic_ctx* c, int64_t cap) {
 	const int nxy = c->g.nx * c->g.ny;
-	return (size_t)(alignUp((int64_t)(nxy + 1) * 4, 128) + cap * 64 + alignUp(cap, 128));
+	return (size_t)(alignUp((int64_t)(nxy * 9 + 1) * 4, 128) + cap * 64);
 }
 
 int64_t wantedMsgCap(const ipic_ctx* c) {
@@ -1002,21 +1063,20 @@ int waitPeersDoneWithCellJ(ipic_ctx* c) {
 // pack both faces of generation `out` into the send buffers and report the totals to the host (boundary stream)
 int packFaces(ipic_ctx* c, int stepIndex) {
 	const int out = c->cur ^ 1;
-	launch_face_pack(c->g, c->buf[out], c->dCellStart, c->dLeave, c->dTag, c->dFaceCnt, faceView(c, c->sendMsg[0], c->sendCap),
+	launch_face_pack(c->g, c->buf[out], c->dCellStart, c->dLeave, c->dTag, c->dOrder, c->dDirOff, c->dFaceCnt, faceView(c, c->sendMsg[0], c->sendCap),
 	                 faceView(c, c->sendMsg[1], c->sendCap), c->dTotals, c->dStop, stepIndex, c->bStream);
 	c->launches += 3;
 	CK(cudaMemcpyAsync(c->hTotals, c->dTotals, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->bStream));
 	return IPIC_OK;
 }
 
-// the pieces of one face message that actually hold data: column offsets, `total` particle records, `total` tags
-struct FacePieces { void* p[3]; size_t bytes[3]; };
+// the pieces of one face message that actually hold data: (column, direction) offsets and `total` particle records
+struct FacePieces { void* p[2]; size_t bytes[2]; };
 FacePieces piecesOf(const ipic_ctx* c, char* base, int cap, int total) {
 	const FaceMsg m = faceView(c, base, cap);
 	FacePieces f;
-	f.p[0] = m.offsets;   f.bytes[0] = (size_t)(c->g.nx * c->g.ny + 1) * sizeof(int);
+	f.p[0] = m.offsets;   f.bytes[0] = (size_t)(c->g.nx * c->g.ny * 9 + 1) * sizeof(int);
 	f.p[1] = m.particles; f.bytes[1] = (size_t)total * 64;
-	f.p[2] = m.tags;      f.bytes[2] = (size_t)total;
 	return f;
 }
 
@@ -1048,15 +1108,18 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 			CK(cudaStreamWaitEvent(c->bStream, neighbour(c, -1)->evRecv, 0));
 			CK(cudaStreamWaitEvent(c->bStream, neighbour(c, +1)->evRecv, 0));
 		}
-		launch_move(moveArgs(c, f, 0, 1), c->bStream);
-		c->launches++;
-		if (lz > 1) { launch_move(moveArgs(c, f, lz - 1, 1), c->bStream); c->launches++; }
+		if (lz > 1 && !c->chunked) {
+			c->launches += launch_move(moveArgs(c, f, 0, 2, lz - 1), c->bStream);      // both boundary planes in one launch
+		} else {
+			c->launches += launch_move(moveArgs(c, f, 0, 1), c->bStream);
+			if (lz > 1) c->launches += launch_move(moveArgs(c, f, lz - 1, 1), c->bStream);
+		}
 		if (f.migrate) { int rc = packFaces(c, stepIndex); if (rc) return rc; }
 		CK(cudaEventRecord(c->evPacked, c->bStream));
 		break;
 	}
 	case PH_INTERIOR:
-		if (lz > 2) { launch_move(moveArgs(c, f, 1, lz - 2), c->stream); c->launches++; }
+		if (lz > 2) c->launches += launch_move(moveArgs(c, f, 1, lz - 2), c->stream);
 		if (f.fuseDeposit) CK(cudaEventRecord(c->evMoved, c->stream));
 		break;
 	case PH_EXCHANGE: {
@@ -1066,12 +1129,12 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 		const FacePieces rDown = piecesOf(c, c->recvMsg[0], c->recvCap, t[2]), rUp = piecesOf(c, c->recvMsg[1], c->recvCap, t[3]);
 		CK(cudaStreamWaitEvent(c->commStream, c->evPacked, 0));
 		if (c->comm) {
-			CommPiece sends[6], recvs[6];
-			for (int k = 0; k < 3; k++) {
-				sends[k] = { sUp.p[k], sUp.bytes[k], +1 };   sends[3 + k] = { sDown.p[k], sDown.bytes[k], -1 };
-				recvs[k] = { rDown.p[k], rDown.bytes[k], -1 }; recvs[3 + k] = { rUp.p[k], rUp.bytes[k], +1 };
+			CommPiece sends[4], recvs[4];
+			for (int k = 0; k < 2; k++) {
+				sends[k] = { sUp.p[k], sUp.bytes[k], +1 };   sends[2 + k] = { sDown.p[k], sDown.bytes[k], -1 };
+				recvs[k] = { rDown.p[k], rDown.bytes[k], -1 }; recvs[2 + k] = { rUp.p[k], rUp.bytes[k], +1 };
 			}
-			int rc = comm_sendrecv(c->comm, sends, 6, recvs, 6, c->commStream, g_lastError);
+			int rc = comm_sendrecv(c->comm, sends, 4, recvs, 4, c->commStream, g_lastError);
 			if (rc) return rc;
 		} else {
 			ipic_ctx* down = neighbour(c, -1);
@@ -1079,7 +1142,7 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 			CK(cudaStreamWaitEvent(c->commStream, down->evPacked, 0));
 			CK(cudaStreamWaitEvent(c->commStream, up->evPacked, 0));
 			const FacePieces fromDown = piecesOf(down, down->sendMsg[1], down->sendCap, t[2]), fromUp = piecesOf(up, up->sendMsg[0], up->sendCap, t[3]);
-			for (int k = 0; k < 3; k++) {
+			for (int k = 0; k < 2; k++) {
 				if (rDown.bytes[k]) CK(cudaMemcpyPeerAsync(rDown.p[k], c->device, fromDown.p[k], down->device, rDown.bytes[k], c->commStream));
 				if (rUp.bytes[k]) CK(cudaMemcpyPeerAsync(rUp.p[k], c->device, fromUp.p[k], up->device, rUp.bytes[k], c->commStream));
 			}
@@ -1104,8 +1167,8 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 				CK(cudaStreamWaitEvent(c->stream, c->evRecv, 0));
 			}
 			ProfSpan span(c, 1);
-			importPlanes(c, stepIndex, 0, 1, lz == 1);
-			if (lz > 1) importPlanes(c, stepIndex, lz - 1, 1, true);
+			if (lz > 1) importPlanes(c, stepIndex, 0, 2, true, lz - 1);      // both boundary planes in one launch
+			else importPlanes(c, stepIndex, 0, 1, true);
 		} else {
 			CK(cudaMemcpyAsync(c->dCount, c->dStay, (size_t)c->g.ncellsLocal * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
 		}
@@ -1151,6 +1214,8 @@ int confirmSlabStep(ipic_ctx* c, bool* recovered) {
 	*recovered = false;
 	CK(cudaSetDevice(c->device));
 	CK(cudaEventSynchronize(c->evStepDone));
+	// (the sticky word is never cleared on slabs: a slab that once needed the sort pass keeps it)
+	c->sortLikely = c->hStop[5] != 0;
 	if (!c->hStop[0]) return IPIC_OK;
 	if (c->hStop[3]) return stopError(c, c->hStop);
 	const int failed = c->hStop[1];
@@ -1273,7 +1338,7 @@ int runSlabSteps(ipic_ctx** ctxs, int n, uint64_t numSteps, uint32_t flags, doub
 			ipic_ctx* c = ctxs[r];
 			CK(cudaSetDevice(c->device));
 			if (s == 0) CK(cudaEventRecord(ev[(size_t)r * 3 + 1], c->stream));
-			CK(cudaMemcpyAsync(c->hStop, c->dStop, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+			CK(cudaMemcpyAsync(c->hStop, c->dStop, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 			CK(cudaEventRecord(c->evStepDone, c->stream));
 		}
 	}
@@ -1332,8 +1397,10 @@ static int finishSingleBatch(ipic_ctx* c, int genAtStart, uint64_t numSteps, uin
 		}
 		firstBatch = false;
 		if (c->profiling) { int rc = drainProfile(c); if (rc) return rc; }
-		int stop[4];
+		int stop[8];
 		CK(cudaMemcpy(stop, c->dStop, sizeof stop, cudaMemcpyDeviceToHost));
+		c->sortLikely = stop[5] != 0;
+		if (stop[5]) CK(cudaMemset(c->dStop + 5, 0, sizeof(int)));
 		if (!stop[0]) return IPIC_OK;
 		// import of step `stop[1]` of this batch overflowed; later steps were skipped on the device
 		const int failed = stop[1];

@@ -78,6 +78,100 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // streaming (write-once) stores: let L2 evict first
 __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
 
+// ---- direction-sorted index of a cell's outbox ----------------------------------------------------
+//
+// The import wants, for a target cell and a direction, "the entries of that neighbour's outbox with tag t".  Instead of
+// letting all 26 neighbours scan all tags of an outbox, a stable counting sort of every outbox is left behind:
+//   dirOff[t], t = 0..27 : number of entries with a tag below t (dirOff[27] = L, the number of leavers)
+//   order[i], i < L      : the outbox entry (0 = first leaver of the cell) that is i-th in (tag, outbox order)
+// Up to 32 leavers (every cell of the uniform plasma) the mover does it itself, in the registers of one warp, from the tags
+// it still has in shared memory (sort_outbox_small).  Fuller outboxes are only MARKED by the mover (dirOff[0] = -2) and
+// sorted by k_sort_outbox right after it, one warp per marked cell: measured on the dipole deck (~90 leavers per cell), a
+// mover CTA that sits on its registers and shared memory while its warps sort costs 30-120 us per step, the separate
+// kernel about 10.  Outboxes beyond kSortCap entries, and those of the chunked mover, carry dirOff[*] = -1: "not
+// indexed, scan the tags".
+constexpr int kSortCap = 2048;
+constexpr int kSortPending = -2;
+
+// called by ONE warp once the (at most 32) tags of the cell are in sTags
+__device__ __forceinline__ void sort_outbox_small(const unsigned char* sTags, int L, int lane,
+                                                  unsigned short* __restrict__ order, int* __restrict__ dirOff, int* __restrict__ sortFlag) {
+	if (L > 32) {
+		// (the flag is ONE word for the whole grid: tens of thousands of CTAs storing to it serialise in its L2 slice at ~9 ns
+		// apiece -- measured +0.28 ms on the dipole deck -- so it is written only by the few CTAs that still read it as 0)
+		// sortFlag[0]: this step's k_sort_outbox has work (reset by k_commit_flag); sortFlag[1]: sticky, for the host's decision
+		// whether to launch k_sort_outbox at all in the following steps (ipic_ctx::sortLikely)
+		if (lane == 0) {
+			dirOff[0] = kSortPending;
+			if (*(volatile int*)sortFlag == 0) *sortFlag = 1;
+			if (*(volatile int*)(sortFlag + 1) == 0) sortFlag[1] = 1;
+		}
+		return;
+	}
+	// rank of entry `lane` = entries with a smaller tag + earlier entries with the same tag
+	const unsigned t = lane < L ? sTags[lane] : 255u;
+	int below = 0, offd = 0;
+	for (int k = 0; k < L; k++) {
+		const unsigned tk = __shfl_sync(0xffffffffu, t, k);
+		below += tk < t;
+		offd += tk < (unsigned)lane;
+	}
+	const unsigned peers = __match_any_sync(0xffffffffu, t);
+	if (lane < L) order[below + __popc(peers & ((1u << lane) - 1u))] = (unsigned short)lane;
+	if (lane < 28) dirOff[lane] = offd;
+}
+
+// one warp per cell of the planes zBegin, zBegin + zStride, ...; only cells the mover marked are touched
+__global__ void __launch_bounds__(256)
+k_sort_outbox(const Geometry g, const int64_t* __restrict__ cellStart, const int* __restrict__ nLeave, const unsigned char* __restrict__ tag,
+              unsigned short* __restrict__ order, int* __restrict__ dirOff, const int* __restrict__ stopFlag, const int* __restrict__ sortFlag,
+              int zBegin, int zCount, int zStride) {
+	__shared__ int sHistAll[8][28];
+	if (*stopFlag || !*sortFlag) return;
+	const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+	int* sHist = sHistAll[wp];
+	const unsigned lt = (1u << lane) - 1u;
+	const int tasks = g.nx * g.ny * zCount;
+	for (int task = blockIdx.x * 8 + wp; task < tasks; task += gridDim.x * 8) {
+	const int xy = task / zCount;
+	const int cell = xy * g.lz + zBegin + (task - xy * zCount) * zStride;
+	int* off = dirOff + (int64_t)cell * 28;
+	if (off[0] != kSortPending) continue;
+	const int L = nLeave[cell];
+	if (L > kSortCap) {
+		if (lane < 28) off[lane] = -1;
+		continue;
+	}
+	__syncwarp();
+	const int64_t start = cellStart[cell], send = cellStart[cell + 1] - 1;      // outbox entry j lives at slot send - j
+	if (lane < 28) sHist[lane] = 0;
+	__syncwarp();
+	for (int j0 = 0; j0 < L; j0 += 32) {
+		const int j = j0 + lane;
+		const unsigned t = j < L ? tag[send - j] : 255u;
+		const unsigned peers = __match_any_sync(0xffffffffu, t);
+		if (j < L && (peers & lt) == 0u) sHist[t] += __popc(peers);          // one lane per tag value: no conflicts
+		__syncwarp();
+	}
+	const int v = lane < 27 ? sHist[lane] : 0;
+	int incl = v;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+	__syncwarp();
+	if (lane < 28) { sHist[lane] = incl - v; off[lane] = incl - v; }          // lane 27: v = 0, incl = L
+	__syncwarp();
+	for (int j0 = 0; j0 < L; j0 += 32) {
+		const int j = j0 + lane;
+		const unsigned t = j < L ? tag[send - j] : 255u;
+		const unsigned peers = __match_any_sync(0xffffffffu, t);
+		if (j < L) order[start + sHist[t] + __popc(peers & lt)] = (unsigned short)j;
+		__syncwarp();
+		if (j < L && (peers & lt) == 0u) sHist[t] += __popc(peers);
+		__syncwarp();
+	}
+	}
+}
+
 // ---- fused mover + classify (+ deposit) ----------------------------------------------------------
 //
 // One CTA of 128 threads per cell; a tile is ITEMS x 128 consecutive particles of the cell = ITEMS x 4
@@ -100,8 +194,9 @@ template<int NF, bool INTERP, bool DEPOSIT, bool MIGRATE, bool PUSH>
 __global__ void __launch_bounds__(kBlock, DEPOSIT ? IPIC_MINB_DEP : IPIC_MINB_NODEP)
 k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, const int64_t* __restrict__ cellStart,
        const int* __restrict__ countIn, int* __restrict__ countOut, int* __restrict__ nLeave,
-       unsigned char* __restrict__ tag, const double* __restrict__ fieldEB, double* __restrict__ cellJ,
-       const int* __restrict__ stopFlag, int zBegin, int zCount, int stages) {
+       unsigned char* __restrict__ tag, unsigned short* __restrict__ order, int* __restrict__ dirOff,
+       const double* __restrict__ fieldEB, double* __restrict__ cellJ,
+       const int* __restrict__ stopFlag, int* __restrict__ sortFlag, int zBegin, int zCount, int zStride, int stages) {
 
 	constexpr int ITEMS = 1;                                     // particles per thread per tile (one wins: more resident warps)
 	constexpr int TILE = ITEMS * kBlock;
@@ -112,7 +207,7 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int xy = blockIdx.x / zCount;
-	const int zl = zBegin + (blockIdx.x - xy * zCount);          // owned z-plane within the slab
+	const int zl = zBegin + (blockIdx.x - xy * zCount) * zStride;   // owned z-plane within the slab (planes zBegin, zBegin + zStride, ...)
 	const int cx = xy / g.ny, cy = xy - cx * g.ny, cz = g.z0 + zl;
 	const int cell = xy * g.lz + zl;
 
@@ -124,6 +219,7 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	__shared__ double sRed[DEPOSIT ? 8 * kRedRow : 1];           // deposit reduction: 8 sums x 128 partials per pass
 	__shared__ double sJ[24];                                    // the cell's 8x3 corner sums
 	__shared__ double sGeo[6];                                   // cell origin, cell centre
+	__shared__ unsigned char sTags[32];                          // tags of the first 32 outbox entries, for sort_outbox_small
 
 	const int n = countIn[cell];
 	const int64_t base = cellStart[cell];
@@ -316,8 +412,10 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 					int d;
 					if (st) d = kept + (mine[k] & 0xffff) + __popc(bs[k] & lt);
 					else {
-						d = cap - 1 - (left + (mine[k] >> 16) + __popc(bl[k] & lt));
+						const int j = left + (mine[k] >> 16) + __popc(bl[k] & lt);       // outbox entry
+						d = cap - 1 - j;
 						tag[base + d] = (unsigned char)code[k];
+						if (j < 32) sTags[j] = (unsigned char)code[k];
 					}
 					double* q = dst + (int64_t)(d >> 5) * BLOCK_DOUBLES + (d & 31);
 					st_stream(q, px[k]); st_stream(q + 32, py[k]); st_stream(q + 64, pz[k]);
@@ -332,6 +430,10 @@ k_move(const Geometry g, const ParticleArrays in, const ParticleArrays out, cons
 	}
 	if (PUSH && tid == 0) { countOut[cell] = kept; nLeave[cell] = left; }
 	if (DEPOSIT && tid < 24) cellJ[cellj_index(g, cx, cy, cz) + tid] = sJ[tid];      // GLOBAL cell id, z-major: a slab is contiguous
+	if (MIGRATE && PUSH) {
+		__syncthreads();                                         // the tags of the cell's first leavers are in sTags
+		if (warp == 0) sort_outbox_small(sTags, left, lane, order + base, dirOff + (int64_t)cell * 28, sortFlag);
+	}
 }
 
 // ---- fused mover + deposit, warp-specialised ---------------------------------------------------------
@@ -355,7 +457,8 @@ template<int NF, bool MIGRATE>
 __global__ void __launch_bounds__(kBlock + 32, IPIC_MINB_WS)
 k_move_ws(const Geometry g, const ParticleArrays in, const ParticleArrays out, const int64_t* __restrict__ cellStart,
           const int* __restrict__ countIn, int* __restrict__ countOut, int* __restrict__ nLeave,
-          unsigned char* __restrict__ tag, double* __restrict__ cellJ, const int* __restrict__ stopFlag, int zBegin, int zCount, int stages) {
+          unsigned char* __restrict__ tag, unsigned short* __restrict__ order, int* __restrict__ dirOff,
+          double* __restrict__ cellJ, const int* __restrict__ stopFlag, int* __restrict__ sortFlag, int zBegin, int zCount, int zStride, int stages) {
 
 	constexpr int TILE = kBlock;
 	constexpr int TILE_DOUBLES = TILE * NF;
@@ -365,7 +468,7 @@ k_move_ws(const Geometry g, const ParticleArrays in, const ParticleArrays out, c
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int xy = blockIdx.x / zCount;
-	const int zl = zBegin + (blockIdx.x - xy * zCount);
+	const int zl = zBegin + (blockIdx.x - xy * zCount) * zStride;
 	const int cx = xy / g.ny, cy = xy - cx * g.ny, cz = g.z0 + zl;
 	const int cell = xy * g.lz + zl;
 
@@ -373,6 +476,7 @@ k_move_ws(const Geometry g, const ParticleArrays in, const ParticleArrays out, c
 	__shared__ uint64_t sFull[kMaxStages], sEmpty[kMaxStages];
 	__shared__ int sCnt[2][kWarps];                              // per push warp: stayers | leavers << 16
 	__shared__ double sGeo[6];                                   // cell origin, cell centre
+	__shared__ unsigned char sTags[32];                          // tags of the first 32 outbox entries, for sort_outbox_small
 
 	const int n = countIn[cell];
 	const int64_t base = cellStart[cell];
@@ -524,8 +628,10 @@ k_move_ws(const Geometry g, const ParticleArrays in, const ParticleArrays out, c
 			int d;
 			if (st) d = kept + (mine & 0xffff) + __popc(bs & lt);
 			else {
-				d = cap - 1 - (left + (mine >> 16) + __popc(bl & lt));
+				const int j = left + (mine >> 16) + __popc(bl & lt);                 // outbox entry
+				d = cap - 1 - j;
 				tag[base + d] = (unsigned char)code;
+				if (j < 32) sTags[j] = (unsigned char)code;
 			}
 			double* q = dst + (int64_t)(d >> 5) * BLOCK_DOUBLES + (d & 31);
 			st_stream(q, px); st_stream(q + 32, py); st_stream(q + 64, pz);
@@ -537,6 +643,10 @@ k_move_ws(const Geometry g, const ParticleArrays in, const ParticleArrays out, c
 		if (++s == stages) { s = 0; phase ^= 1; }
 	}
 	if (tid == 0) { countOut[cell] = kept; nLeave[cell] = left; }
+	if (MIGRATE) {
+		asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");        // the push warps: the tags of the cell's first leavers are in sTags
+		if (warp == 0) sort_outbox_small(sTags, left, lane, order + base, dirOff + (int64_t)cell * 28, sortFlag);
+	}
 }
 
 // ---- chunked mover: several CTAs per cell ----------------------------------------------------------
@@ -578,7 +688,7 @@ k_move_chunk(const Geometry g, const ParticleArrays in, const ParticleArrays out
              const int* __restrict__ countIn, int* __restrict__ countOut, int* __restrict__ nLeave,
              unsigned char* __restrict__ tag, const double* __restrict__ fieldEB, double* __restrict__ cellJ, double* chunkJ,
              const int* __restrict__ stopFlag, const int2* __restrict__ chunkTable, int rangeStart, unsigned* ticket,
-             unsigned long long* status) {
+             unsigned long long* status, int* __restrict__ dirOff) {
 
 	constexpr int BLOCK_DOUBLES = 32 * NF;
 	if (*stopFlag) return;
@@ -609,6 +719,7 @@ k_move_chunk(const Geometry g, const ParticleArrays in, const ParticleArrays out
 	const int cnt = min(kChunk, n - lo);
 	if (cnt <= 0 && !(j == 0 && n == 0)) return;                 // chunk beyond the population: nobody waits for it
 	const bool last = lo + kChunk >= n;                          // the cell's last populated chunk
+	if (MIGRATE && last && tid < 28) dirOff[(int64_t)cell * 28 + tid] = -1;       // outboxes of this kernel carry no direction index: the import scans their tags
 	const int64_t base = cellStart[cell];
 	const int cap = (int)(cellStart[cell + 1] - base);
 	double* __restrict__ dst = out.d + base * NF;
@@ -819,63 +930,64 @@ k_move_chunk(const Geometry g, const ParticleArrays in, const ParticleArrays out
 //
 // One warp per target cell.  Lane d looks at the neighbour of direction d (lexicographic (0,0,0)..(2,2,2),
 // 13 = self skipped): source cell = target + (a-1,b-1,c-1) with periodic address (transfer_buffer.h,
-// cell.h:1012-1048); the entries of that neighbour's outbox tagged (2-a,2-b,2-c) are ours.  When no
-// neighbour has more than 32 leavers (the common case) all 26 tag rows are fetched at once, the hits are
-// turned into 26 ballots, and every arrival is copied by its own lane: three dependent memory round
-// trips per cell instead of 2 x 26.
+// cell.h:1012-1048); the entries of that neighbour's outbox tagged (2-a,2-b,2-c) = 26 - d are ours.
+//
+// The movers leave a DIRECTION-SORTED INDEX of every outbox behind (sort_outbox): dirOff[cell][t] = number of
+// entries with a tag below t, order[cellStart + i] = the outbox entry that is i-th in (tag, outbox order).  Lane d
+// therefore reads two integers to learn how many particles arrive from its neighbour and where they are -- no tag
+// is scanned, and only particles that really arrive are touched.  An exclusive scan over the lanes puts the
+// directions in canonical order, every lane lists its arrivals in a shared-memory window, and the warp copies 32
+// arrivals per trip.  Neighbours whose outbox carries no index (more than kSortCap leavers, or written by the
+// chunked mover) are scanned tag by tag, direction after direction.
 //
 // SLAB: the universe is split into z-slabs; a neighbour below the slab's first plane / above its last
 // one lives on another GPU, and its outbox is the matching column of the face message received from
-// that GPU (k_face_copy: same entries, same order, AoS payload).
+// that GPU (k_face_copy), where the entries of one direction are contiguous.
 
 #ifndef IPIC_IMPORT_BLOCK
 #define IPIC_IMPORT_BLOCK 256
 #endif
 #ifndef IPIC_IMPORT_MINB
-#define IPIC_IMPORT_MINB 4       // resident CTAs per SM the import is compiled for (B200 sweep: 3 -> 72 us, 4 -> 56 us, 8 -> 68 us)
+#define IPIC_IMPORT_MINB 4       // resident CTAs per SM the import is compiled for
 #endif
 constexpr int kImportBlock = IPIC_IMPORT_BLOCK;
 constexpr int kImportWarps = kImportBlock / 32;
-constexpr int kMedRounds = 16;             // the medium path of the import handles outboxes of up to 32 * kMedRounds entries
+constexpr int kListWindow = 256;           // arrivals listed per pass of a warp
 
-// outbox entry j of a source: local outboxes grow backwards from the end of the cell's segment,
-// message columns forwards from the column's first entry
-struct ImportSource {
-	const unsigned char* tags;
-	const double* data;
-	bool remote;
-	int nf;
-	__device__ __forceinline__ unsigned char tagOf(int64_t base, int j) const { return remote ? tags[base + j] : tags[base - j]; }
-	__device__ __forceinline__ void copyTo(int64_t base, int j, double* __restrict__ t) const {
-		double v[kFields];
-		if (remote) {                                    // message records always carry all 8 fields
-			const double2* s = reinterpret_cast<const double2*>(data + (base + j) * kFields);
-			#pragma unroll
-			for (int f = 0; f < kFields; f += 2) { const double2 x = s[f >> 1]; v[f] = x.x; v[f + 1] = x.y; }
-		} else {
-			const double* s = data + slot_index(base - j, nf);
-			#pragma unroll
-			for (int f = 0; f < kFields; f++) if (f < nf) v[f] = s[f * kFieldStride];
-		}
+// one arrival: fields of record `rec` of a face message (AoS, always 8 fields) or of slot `slot` of generation src
+__device__ __forceinline__ void copy_arrival(bool remote, const double* __restrict__ msg, int64_t rec, const double* __restrict__ srcd, int64_t slot,
+                                             int nf, double* __restrict__ t) {
+	double v[kFields];
+	if (remote) {
+		const double2* s = reinterpret_cast<const double2*>(msg + rec * kFields);
 		#pragma unroll
-		for (int f = 0; f < kFields; f++) if (f < nf) t[f * kFieldStride] = v[f];
+		for (int f = 0; f < kFields; f += 2) { const double2 x = s[f >> 1]; v[f] = x.x; v[f + 1] = x.y; }
+	} else {
+		const double* s = srcd + slot_index(slot, nf);
+		#pragma unroll
+		for (int f = 0; f < kFields; f++) if (f < nf) v[f] = s[f * kFieldStride];
 	}
-};
+	#pragma unroll
+	for (int f = 0; f < kFields; f++) if (f < nf) t[f * kFieldStride] = v[f];
+}
 
 template<bool SLAB>
 __global__ void __launch_bounds__(kImportBlock, IPIC_IMPORT_MINB)
 k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__ srcStart, const int* __restrict__ srcLeave,
-         const unsigned char* __restrict__ tag, const ParticleArrays dst, const int64_t* __restrict__ dstStart,
-         const int* __restrict__ stay, int* __restrict__ dstCount, int reserveOwnOutbox, int* __restrict__ stopFlag, int stepIndex, int zBegin, int zCount,
+         const unsigned char* __restrict__ tag, const unsigned short* __restrict__ order, const int* __restrict__ dirOff,
+         const ParticleArrays dst, const int64_t* __restrict__ dstStart,
+         const int* __restrict__ stay, int* __restrict__ dstCount, int reserveOwnOutbox, int* __restrict__ stopFlag, int stepIndex, int zBegin, int zCount, int zStride,
          const FaceMsg fromDown, const FaceMsg fromUp) {
 
-	__shared__ unsigned sMaskAll[kImportWarps][kMedRounds][27];      // medium path: match masks per (round, direction), one set per warp
+	__shared__ int sListAll[kImportWarps][kListWindow];       // arrivals of the current window: direction << 24 | index within the direction
+	__shared__ int64_t sSrcA[kImportWarps][27];               // per direction: first order slot (local) / first record (remote)
+	__shared__ int64_t sSrcB[kImportWarps][27];               // per direction: last slot of the neighbour's segment (local)
 	if (*(volatile int*)stopFlag) return;
-	const int lane = threadIdx.x & 31;
-	const int task = blockIdx.x * kImportWarps + (threadIdx.x >> 5);
+	const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+	const int task = blockIdx.x * kImportWarps + wp;
 	if (task >= g.nx * g.ny * zCount) return;
 	const int xy = task / zCount;
-	const int zl = zBegin + (task - xy * zCount);
+	const int zl = zBegin + (task - xy * zCount) * zStride;
 	const int cx = xy / g.ny, cy = xy - cx * g.ny;
 	const int cell = xy * g.lz + zl;
 
@@ -884,35 +996,30 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 	const int room = dcap - (reserveOwnOutbox ? srcLeave[cell] : 0);
 	int w = stay[cell];
 
-	// source of direction d (uniform over the warp): the local outbox, or a column of a face message
-	auto sourceOf = [&](int d) {
-		ImportSource s;
-		s.nf = g.nf;
-		const int c = d % 3;
-		s.remote = SLAB && ((c == 0 && zl == 0) || (c == 2 && zl == g.lz - 1));
-		if (s.remote) { const FaceMsg& m = c == 0 ? fromDown : fromUp; s.tags = m.tags; s.data = m.particles; }
-		else { s.tags = tag; s.data = src.d; }
-		return s;
-	};
+	auto isRemote = [&](int d) { const int c = d % 3; return SLAB && ((c == 0 && zl == 0) || (c == 2 && zl == g.lz - 1)); };
 
-	// lane d: its neighbour's outbox (number of entries, index base)
-	int myLeave = 0;
-	int64_t myBase = 0;
-	bool corrupt = false;
+	// lane d: what arrives from its neighbour
+	int cnt = 0, scell = 0;
+	int64_t A = 0, B = 0;
+	bool unsorted = false, corrupt = false;
 	if (lane < 27 && lane != 13) {
 		const int a = lane / 9, b = (lane / 3) % 3, c = lane % 3;
 		const int sx = (cx + a - 1 + g.nx) % g.nx, sy = (cy + b - 1 + g.ny) % g.ny;
-		if (SLAB && ((c == 0 && zl == 0) || (c == 2 && zl == g.lz - 1))) {
+		if (isRemote(lane)) {
 			const FaceMsg& m = c == 0 ? fromDown : fromUp;
-			const int first = m.offsets[sx * g.ny + sy];
-			myLeave = m.offsets[sx * g.ny + sy + 1] - first;
-			myBase = first;
-			if (first < 0 || myLeave < 0 || first + myLeave > m.cap) { corrupt = true; myLeave = 0; }
+			const int* o = m.offsets + (sx * g.ny + sy) * 9 + (2 - a) * 3 + (2 - b);
+			const int first = o[0];
+			cnt = o[1] - first;
+			A = first;
+			if (first < 0 || cnt < 0 || first + cnt > m.cap) { corrupt = true; cnt = 0; }
 		} else {
 			const int szl = (zl + c - 1 + g.lz) % g.lz;
-			const int scell = (sx * g.ny + sy) * g.lz + szl;
-			myLeave = srcLeave[scell];
-			myBase = srcStart[scell + 1] - 1;             // outbox entry j lives at slot myBase - j
+			scell = (sx * g.ny + sy) * g.lz + szl;
+			const int* o = dirOff + (int64_t)scell * 28 + (26 - lane);
+			const int o0 = o[0];
+			B = srcStart[scell + 1] - 1;                  // outbox entry j lives at slot B - j
+			if (o0 < 0) unsorted = true;
+			else { cnt = o[1] - o0; A = srcStart[scell] + o0; }
 		}
 	}
 	if (SLAB && __any_sync(0xffffffffu, corrupt)) {
@@ -920,116 +1027,67 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 		if (lane == 0) { atomicMin(stopFlag + 1, stepIndex); atomicExch(stopFlag + 3, 2); atomicExch(stopFlag, 1); }
 		return;
 	}
-	const int maxLeave = __reduce_max_sync(0xffffffffu, myLeave);
-	if (maxLeave == 0) {
-		if (lane == 0) dstCount[cell] = w;
-		return;
-	}
 
-	if (maxLeave <= 32) {
-		unsigned mask[27];
-		{
-			unsigned char t[27];
-			#pragma unroll
-			for (int d = 0; d < 27; d++) {
-				if (d == 13) continue;
-				const int nl = __shfl_sync(0xffffffffu, myLeave, d);
-				const int64_t base = __shfl_sync(0xffffffffu, myBase, d);
-				t[d] = lane < nl ? sourceOf(d).tagOf(base, lane) : kTagNone;
-			}
-			#pragma unroll
-			for (int d = 0; d < 27; d++) {
-				if (d == 13) { mask[d] = 0; continue; }
-				const unsigned want = (unsigned)((2 - d / 9) * 9 + (2 - (d / 3) % 3) * 3 + (2 - d % 3));
-				mask[d] = __ballot_sync(0xffffffffu, t[d] == want);
-			}
-		}
-		int total = 0;
-		#pragma unroll
-		for (int d = 0; d < 27; d++) total += __popc(mask[d]);
-		for (int i0 = 0; i0 < total; i0 += 32) {
-			const int i = i0 + lane;
-			int pre = 0, dsel = 0, jsel = 0;
-			#pragma unroll
-			for (int d = 0; d < 27; d++) {
-				const int cnt = __popc(mask[d]);
-				if (i >= pre && i < pre + cnt) { dsel = d; jsel = (int)__fns(mask[d], 0, i - pre + 1); }
-				pre += cnt;
-			}
-			const int64_t base = __shfl_sync(0xffffffffu, myBase, dsel);
-			if (i < total && w + i < room) sourceOf(dsel).copyTo(base, jsel, dst.d + slot_index(dbase + w + i, g.nf));
-		}
-		w += total;
-	} else if (maxLeave <= 32 * kMedRounds) {
-		// medium flows (up to 512 leavers per neighbour: the dipole decks' ~90, the 8-GPU weak-scaling point's ~34): the
-		// same idea in rounds of 32 entries.  Pass 1 fetches, per round, all 26 tag rows at once and parks the 26 match
-		// masks in shared memory; lane d adds up its direction.  A scan over the lanes gives every direction its place in
-		// the canonical order; pass 2 copies 32 arrivals per trip, each lane finding its (direction, entry) from the masks.
-		unsigned (*sMask)[27] = sMaskAll[threadIdx.x >> 5];
-		const int rounds = (maxLeave + 31) >> 5;
-		int myCount = 0;
-		for (int r = 0; r < rounds; r++) {
-			unsigned char t[27];
-			#pragma unroll
-			for (int d = 0; d < 27; d++) {
-				if (d == 13) continue;
-				const int nl = __shfl_sync(0xffffffffu, myLeave, d);
-				const int64_t base = __shfl_sync(0xffffffffu, myBase, d);
-				const int j = r * 32 + lane;
-				t[d] = j < nl ? sourceOf(d).tagOf(base, j) : kTagNone;
-			}
-			#pragma unroll
-			for (int d = 0; d < 27; d++) {
-				if (d == 13) continue;
-				const unsigned want = (unsigned)((2 - d / 9) * 9 + (2 - (d / 3) % 3) * 3 + (2 - d % 3));
-				const unsigned m = __ballot_sync(0xffffffffu, t[d] == want);
-				if (lane == d) { sMask[r][d] = m; myCount += __popc(m); }
-			}
-		}
-		__syncwarp();
-		int incl = myCount;
+	if (!__any_sync(0xffffffffu, unsorted || cnt >= (1 << 24))) {
+		int incl = cnt;
 		#pragma unroll
 		for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-		const int dirBase = incl - myCount;                   // lane d: first arrival of direction d
+		const int dirBase = incl - cnt;                      // lane d: place of its first arrival in the canonical order
 		const int total = __shfl_sync(0xffffffffu, incl, 31);
-		for (int i0 = 0; i0 < total; i0 += 32) {
-			const int i = i0 + lane;
-			int dsel = 0, rho = 0;
-			#pragma unroll
-			for (int d = 0; d < 27; d++) {
-				if (d == 13) continue;
-				const int b = __shfl_sync(0xffffffffu, dirBase, d), c = __shfl_sync(0xffffffffu, myCount, d);
-				if (i >= b && i < b + c) { dsel = d; rho = i - b; }
-			}
-			int jsel = 0;
-			if (i < total) {
-				for (int r = 0; r < rounds; r++) {
-					const unsigned m = sMask[r][dsel];
-					const int c = __popc(m);
-					if (rho < c) { jsel = r * 32 + (int)__fns(m, 0, rho + 1); break; }
-					rho -= c;
+		if (total == 0) {
+			if (lane == 0) dstCount[cell] = w;
+			return;
+		}
+		int* sList = sListAll[wp];
+		if (lane < 27) { sSrcA[wp][lane] = A; sSrcB[wp][lane] = B; }
+		for (int win0 = 0; win0 < total; win0 += kListWindow) {
+			const int winEnd = min(total, win0 + kListWindow);
+			__syncwarp();
+			for (int p = max(dirBase, win0); p < min(dirBase + cnt, winEnd); p++) sList[p - win0] = (lane << 24) | (p - dirBase);
+			__syncwarp();
+			for (int i0 = win0; i0 < winEnd; i0 += 32) {
+				const int i = i0 + lane;
+				if (i < winEnd && w + i < room) {
+					const int e = sList[i - win0];
+					const int d = e >> 24, k = e & 0xffffff;
+					const int64_t a0 = sSrcA[wp][d];
+					double* t = dst.d + slot_index(dbase + w + i, g.nf);
+					if (isRemote(d)) copy_arrival(true, (d % 3 == 0 ? fromDown : fromUp).particles, a0 + k, nullptr, 0, g.nf, t);
+					else copy_arrival(false, nullptr, 0, src.d, sSrcB[wp][d] - (int64_t)order[a0 + k], g.nf, t);
 				}
 			}
-			const int64_t base = __shfl_sync(0xffffffffu, myBase, dsel);
-			if (i < total && w + i < room) sourceOf(dsel).copyTo(base, jsel, dst.d + slot_index(dbase + w + i, g.nf));
 		}
 		w += total;
 	} else {
-		// general path: direction after direction, 32 outbox entries per round
+		// some neighbour's outbox has no index: direction after direction; indexed / remote ranges are copied, the others scanned
 		for (int d = 0; d < 27; d++) {
 			if (d == 13) continue;
-			const int nl = __shfl_sync(0xffffffffu, myLeave, d);
-			if (nl == 0) continue;
-			const int64_t base = __shfl_sync(0xffffffffu, myBase, d);
-			const ImportSource s = sourceOf(d);
-			const unsigned want = (unsigned)((2 - d / 9) * 9 + (2 - (d / 3) % 3) * 3 + (2 - d % 3));
+			const bool uns = __shfl_sync(0xffffffffu, (int)unsorted, d) != 0;
+			const int64_t a0 = __shfl_sync(0xffffffffu, A, d), b0 = __shfl_sync(0xffffffffu, B, d);
+			if (!uns) {
+				const int n = __shfl_sync(0xffffffffu, cnt, d);
+				const bool remote = isRemote(d);
+				for (int k0 = 0; k0 < n; k0 += 32) {
+					const int k = k0 + lane;
+					if (k < n && w + k < room) {
+						double* t = dst.d + slot_index(dbase + w + k, g.nf);
+						if (remote) copy_arrival(true, (d % 3 == 0 ? fromDown : fromUp).particles, a0 + k, nullptr, 0, g.nf, t);
+						else copy_arrival(false, nullptr, 0, src.d, b0 - (int64_t)order[a0 + k], g.nf, t);
+					}
+				}
+				w += n;
+				continue;
+			}
+			const int sc = __shfl_sync(0xffffffffu, scell, d);
+			const int nl = srcLeave[sc];
+			const unsigned want = (unsigned)(26 - d);
 			for (int j0 = 0; j0 < nl; j0 += 32) {
 				const int j = j0 + lane;
-				const bool hit = j < nl && s.tagOf(base, j) == want;
+				const bool hit = j < nl && tag[b0 - j] == want;
 				const unsigned m = __ballot_sync(0xffffffffu, hit);
 				if (hit) {
 					const int o = w + __popc(m & ((1u << lane) - 1u));
-					if (o < room) s.copyTo(base, j, dst.d + slot_index(dbase + o, g.nf));
+					if (o < room) copy_arrival(false, nullptr, 0, src.d, b0 - j, g.nf, dst.d + slot_index(dbase + o, g.nf));
 				}
 				w += __popc(m);
 			}
@@ -1045,58 +1103,67 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 // failing step still gets its import attempt recorded in dstCount == required size)
 __global__ void k_commit_flag(int* stopFlag) {
 	if (stopFlag[2]) stopFlag[0] = 1;
+	stopFlag[4] = 0;                       // "some outbox needs k_sort_outbox": the movers of the next step raise it again
 }
 
 
-// ---- z-slab faces: pack the leavers that cross the slab boundary, unpack into ghost cells ----------
+// ---- z-slab faces: pack the leavers that cross the slab boundary ------------------------------------
 //
 // Face 0 = the slab's lowest owned z-plane, leavers with direction k = 0 (to the neighbour below);
 // face 1 = the highest owned plane, k = 2 (to the neighbour above).  A face message is
-//   offsets[nx*ny + 1]  exclusive prefix of the entries per (x,y) column, offsets[nx*ny] = total
-//   particles[cap][8]   AoS, columns in (x*ny + y) order, each column in outbox order
-//   tags[cap]           full direction code of every entry
-// i.e. for the receiver's import kernel a column is exactly the outbox it would have found in the
-// neighbour's cell (the reference's transfer buffers of that cell, transfer_buffer.h:15-95), restricted
-// to the entries that can concern it: arrival order stays canonical across slab boundaries.
+//   offsets[nx*ny*9 + 1]  exclusive prefix of the entries per ((x,y) column, (i,j) of the direction code); last = total
+//   particles[cap][8]     AoS, columns in (x*ny + y) order, within a column by direction code, then outbox order
+// i.e. for the receiver's import kernel a column is the outbox it would have found in the neighbour's cell (the
+// reference's transfer buffers of that cell, transfer_buffer.h:15-95), restricted to the entries that can concern
+// it and already sorted by direction: arrival order stays canonical across slab boundaries.
 
 constexpr int kFaceBlock = 256;
 constexpr int kFaceWarps = kFaceBlock / 32;
 
 __global__ void __launch_bounds__(kFaceBlock)
 k_face_count(const Geometry g, const int64_t* __restrict__ cellStart, const int* __restrict__ nLeave,
-             const unsigned char* __restrict__ tag, int* __restrict__ faceCnt, const int* __restrict__ stopFlag) {
+             const unsigned char* __restrict__ tag, const int* __restrict__ dirOff, int* __restrict__ faceCnt, const int* __restrict__ stopFlag) {
 	const int lane = threadIdx.x & 31;
 	const int nxy = g.nx * g.ny;
 	const int task = blockIdx.x * kFaceWarps + (threadIdx.x >> 5);
 	if (task >= 2 * nxy) return;
-	int cnt = 0;
+	int mine = 0;                                        // lane ab < 9: entries of direction code ab*3 + (face ? 2 : 0)
 	if (!*stopFlag) {
 		const int f = task / nxy, xy = task - f * nxy;
 		const int cell = xy * g.lz + (f ? g.lz - 1 : 0);
-		const int nl = nLeave[cell];
-		const int64_t send = cellStart[cell + 1] - 1;
+		const int* off = dirOff + (int64_t)cell * 28;
 		const unsigned want = f ? 2u : 0u;
-		for (int j0 = 0; j0 < nl; j0 += 32) {
-			const int j = j0 + lane;
-			const bool hit = j < nl && (tag[send - j] % 3u) == want;
-			cnt += __popc(__ballot_sync(0xffffffffu, hit));
+		if (off[0] >= 0) {
+			if (lane < 9) mine = off[lane * 3 + want + 1] - off[lane * 3 + want];
+		} else {
+			const int nl = nLeave[cell];
+			const int64_t send = cellStart[cell + 1] - 1;
+			for (int j0 = 0; j0 < nl; j0 += 32) {
+				const int j = j0 + lane;
+				const unsigned t = j < nl ? tag[send - j] : 255u;
+				#pragma unroll
+				for (int ab = 0; ab < 9; ab++) {
+					const int c = __popc(__ballot_sync(0xffffffffu, t == ab * 3 + want));
+					if (lane == ab) mine += c;
+				}
+			}
 		}
 	}
-	if (lane == 0) faceCnt[task] = cnt;
+	if (lane < 9) faceCnt[task * 9 + lane] = mine;
 }
 
-// one CTA of 1024 threads per face: exclusive scan of the column counts into the message header
+// one CTA of 1024 threads per face: exclusive scan of the (column, direction) counts into the message header
 __global__ void __launch_bounds__(1024)
 k_face_scan(const Geometry g, const int* __restrict__ faceCnt, FaceMsg m0, FaceMsg m1, int* __restrict__ totals) {
 	__shared__ int sWarp[32];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int nxy = g.nx * g.ny;
+	const int n = g.nx * g.ny * 9;
 	const FaceMsg m = blockIdx.x ? m1 : m0;
-	const int* cnt = faceCnt + blockIdx.x * nxy;
+	const int* cnt = faceCnt + blockIdx.x * n;
 	int carry = 0;
-	for (int base = 0; base < nxy; base += 1024) {
+	for (int base = 0; base < n; base += 1024) {
 		const int i = base + tid;
-		const int v = i < nxy ? cnt[i] : 0;
+		const int v = i < n ? cnt[i] : 0;
 		int incl = v;
 		#pragma unroll
 		for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
@@ -1109,53 +1176,61 @@ k_face_scan(const Geometry g, const int* __restrict__ faceCnt, FaceMsg m0, FaceM
 			sWarp[lane] = w;
 		}
 		__syncthreads();
-		if (i < nxy) m.offsets[i] = carry + (warp ? sWarp[warp - 1] : 0) + incl - v;
+		if (i < n) m.offsets[i] = carry + (warp ? sWarp[warp - 1] : 0) + incl - v;
 		carry += sWarp[31];
 		__syncthreads();
 	}
 	if (tid == 0) {
-		m.offsets[nxy] = carry;
+		m.offsets[n] = carry;
 		totals[blockIdx.x] = carry;          // the host compares it with the buffer capacity and packs again into a bigger one if needed
 	}
 }
 
 __global__ void __launch_bounds__(kFaceBlock)
 k_face_copy(const Geometry g, const ParticleArrays src, const int64_t* __restrict__ cellStart, const int* __restrict__ nLeave,
-            const unsigned char* __restrict__ tag, FaceMsg m0, FaceMsg m1) {
+            const unsigned char* __restrict__ tag, const unsigned short* __restrict__ order, const int* __restrict__ dirOff, FaceMsg m0, FaceMsg m1) {
 	const int lane = threadIdx.x & 31;
 	const int nxy = g.nx * g.ny;
 	const int task = blockIdx.x * kFaceWarps + (threadIdx.x >> 5);
 	if (task >= 2 * nxy) return;
 	const int f = task / nxy, xy = task - f * nxy;
 	const FaceMsg m = f ? m1 : m0;
-	const int first = m.offsets[xy], total = m.offsets[xy + 1] - first;
-	if (total <= 0) return;
+	const int* mo = m.offsets + xy * 9;
+	if (mo[9] - mo[0] <= 0) return;
 	const int cell = xy * g.lz + (f ? g.lz - 1 : 0);
-	const int nl = nLeave[cell];
-	const int64_t send = cellStart[cell + 1] - 1;
+	const int64_t send = cellStart[cell + 1] - 1, start = cellStart[cell];
+	const int* off = dirOff + (int64_t)cell * 28;
+	const bool sorted = off[0] >= 0;
 	const unsigned want = f ? 2u : 0u;
-	int w = 0;
-	for (int j0 = 0; j0 < nl; j0 += 32) {
-		const int j = j0 + lane;
-		unsigned char t = kTagNone;
-		if (j < nl) t = tag[send - j];
-		const bool hit = j < nl && (t % 3u) == want;
-		const unsigned mask = __ballot_sync(0xffffffffu, hit);
-		if (hit) {
-			const int o = first + w + __popc(mask & ((1u << lane) - 1u));
-			if (o < m.cap) {
-				const double* s = src.d + slot_index(send - j, g.nf);
-				double v[kFields];
-				v[6] = g.uq; v[7] = g.uqom;
-				#pragma unroll
-				for (int k = 0; k < kFields; k++) if (k < g.nf) v[k] = s[k * kFieldStride];
-				double2* d = reinterpret_cast<double2*>(m.particles + (int64_t)o * kFields);
-				#pragma unroll
-				for (int k = 0; k < kFields; k += 2) d[k >> 1] = make_double2(v[k], v[k + 1]);
-				m.tags[o] = t;
+	auto emit = [&](int64_t slot, int o) {
+		if (o >= m.cap) return;
+		const double* s = src.d + slot_index(slot, g.nf);
+		double v[kFields];
+		v[6] = g.uq; v[7] = g.uqom;
+		#pragma unroll
+		for (int k = 0; k < kFields; k++) if (k < g.nf) v[k] = s[k * kFieldStride];
+		double2* d = reinterpret_cast<double2*>(m.particles + (int64_t)o * kFields);
+		#pragma unroll
+		for (int k = 0; k < kFields; k += 2) d[k >> 1] = make_double2(v[k], v[k + 1]);
+	};
+	for (int ab = 0; ab < 9; ab++) {
+		const int first = mo[ab], total = mo[ab + 1] - first;
+		if (total <= 0) continue;
+		const unsigned code = ab * 3 + want;
+		if (sorted) {
+			const int o0 = off[code];
+			for (int k = lane; k < total; k += 32) emit(send - (int64_t)order[start + o0 + k], first + k);
+		} else {
+			const int nl = nLeave[cell];
+			int w = 0;
+			for (int j0 = 0; j0 < nl; j0 += 32) {
+				const int j = j0 + lane;
+				const bool hit = j < nl && tag[send - j] == code;
+				const unsigned mask = __ballot_sync(0xffffffffu, hit);
+				if (hit) emit(send - j, first + w + __popc(mask & ((1u << lane) - 1u)));
+				w += __popc(mask);
 			}
 		}
-		w += __popc(mask);
 	}
 }
 
@@ -1318,8 +1393,8 @@ static void launch_move_k(const MoveArgs& a, int grid, cudaStream_t st) {
 	auto kernel = k_move<NF, INTERP, DEPOSIT, MIGRATE, PUSH>;
 	optin_dynamic_smem(kernel, move_smem_bytes(NF, kMaxStages), configured);
 	const int stages = std::max(1, std::min(a.stages, kMaxStages));
-	kernel<<<grid, kBlock, move_smem_bytes(NF, stages), st>>>(a.g, a.in, a.out, a.cellStart, a.countIn, a.countOut, a.nLeave, a.tag,
-	                                                          a.fieldEB, a.cellJ, a.stopFlag, a.zBegin, a.zCount, stages);
+	kernel<<<grid, kBlock, move_smem_bytes(NF, stages), st>>>(a.g, a.in, a.out, a.cellStart, a.countIn, a.countOut, a.nLeave, a.tag, a.order, a.dirOff,
+	                                                          a.fieldEB, a.cellJ, a.stopFlag, const_cast<int*>(a.stopFlag) + 4, a.zBegin, a.zCount, a.zStride > 0 ? a.zStride : 1, stages);
 }
 
 template<int NF, bool MIGRATE>
@@ -1328,8 +1403,8 @@ static void launch_move_ws(const MoveArgs& a, int grid, cudaStream_t st) {
 	auto kernel = k_move_ws<NF, MIGRATE>;
 	optin_dynamic_smem(kernel, move_smem_bytes(NF, kMaxStages), configured);
 	const int stages = std::max(1, std::min(a.stages, kMaxStages));
-	kernel<<<grid, kBlock + 32, move_smem_bytes(NF, stages), st>>>(a.g, a.in, a.out, a.cellStart, a.countIn, a.countOut, a.nLeave, a.tag,
-	                                                               a.cellJ, a.stopFlag, a.zBegin, a.zCount, stages);
+	kernel<<<grid, kBlock + 32, move_smem_bytes(NF, stages), st>>>(a.g, a.in, a.out, a.cellStart, a.countIn, a.countOut, a.nLeave, a.tag, a.order, a.dirOff,
+	                                                               a.cellJ, a.stopFlag, const_cast<int*>(a.stopFlag) + 4, a.zBegin, a.zCount, a.zStride > 0 ? a.zStride : 1, stages);
 }
 
 static bool use_warp_specialised() {
@@ -1378,7 +1453,7 @@ static void launch_chunk_k(const MoveArgs& a, cudaStream_t st) {
 	cudaMemsetAsync(a.chunkStatus + a.chunkFirst, 0, (size_t)a.chunkCount * sizeof(unsigned long long), st);
 	cudaMemsetAsync(a.chunkTicket, 0, sizeof(unsigned), st);
 	kernel<<<a.chunkCount, kBlock, smem, st>>>(a.g, a.in, a.out, a.cellStart, a.countIn, a.countOut, a.nLeave, a.tag, a.fieldEB, a.cellJ, a.chunkJ,
-	                                          a.stopFlag, a.chunkTable, a.chunkFirst, a.chunkTicket, a.chunkStatus);
+	                                          a.stopFlag, a.chunkTable, a.chunkFirst, a.chunkTicket, a.chunkStatus, a.dirOff);
 }
 
 template<int NF>
@@ -1394,36 +1469,45 @@ static void launch_chunk_i(const MoveArgs& a, cudaStream_t st) {
 
 int chunk_particles() { return kChunk; }
 
-void launch_move(const MoveArgs& a, cudaStream_t st) {
+int launch_move(const MoveArgs& a, cudaStream_t st) {
 	if (a.chunked && a.push) {
-		if (a.chunkCount <= 0) return;
+		if (a.chunkCount <= 0) return 0;
 		if (a.g.nf == 6) launch_chunk_i<6>(a, st);
 		else launch_chunk_i<8>(a, st);
-		return;
+		return 1;
 	}
 	if (a.g.nf == 6) launch_move_i<6>(a, st);
 	else launch_move_i<8>(a, st);
+	if (!(a.push && a.migrate && a.sortPass)) return 1;
+	// outboxes of more than 32 entries were only marked: sort them now (returns at once when the movers marked none).  Without
+	// this pass the import still works: it scans the tags of marked outboxes like those of the chunked mover.
+	const int tasks = a.g.nx * a.g.ny * a.zCount;
+	if (tasks == 0) return 1;
+	k_sort_outbox<<<std::min((tasks + 7) / 8, 148 * 8), 256, 0, st>>>(a.g, a.cellStart, a.nLeave, a.tag, a.order, a.dirOff, a.stopFlag, a.stopFlag + 4,
+	                                              a.zBegin, a.zCount, a.zStride > 0 ? a.zStride : 1);
+	return 2;
 }
 
 void launch_import(const ImportArgs& a, bool commit, cudaStream_t st) {
 	const int tasks = a.g.nx * a.g.ny * a.zCount;
 	if (tasks == 0) return;
 	const int grid = (tasks + kImportWarps - 1) / kImportWarps;
-	if (a.slab) k_import<true><<<grid, kImportBlock, 0, st>>>(a.g, a.src, a.srcStart, a.srcLeave, a.tag, a.dst, a.dstStart, a.stay, a.dstCount,
-	                                                        a.reserveOwnOutbox, a.stopFlag, a.stepIndex, a.zBegin, a.zCount, a.fromDown, a.fromUp);
-	else k_import<false><<<grid, kImportBlock, 0, st>>>(a.g, a.src, a.srcStart, a.srcLeave, a.tag, a.dst, a.dstStart, a.stay, a.dstCount,
-	                                                    a.reserveOwnOutbox, a.stopFlag, a.stepIndex, a.zBegin, a.zCount, FaceMsg{}, FaceMsg{});
+	if (a.slab) k_import<true><<<grid, kImportBlock, 0, st>>>(a.g, a.src, a.srcStart, a.srcLeave, a.tag, a.order, a.dirOff, a.dst, a.dstStart, a.stay, a.dstCount,
+	                                                        a.reserveOwnOutbox, a.stopFlag, a.stepIndex, a.zBegin, a.zCount, a.zStride > 0 ? a.zStride : 1, a.fromDown, a.fromUp);
+	else k_import<false><<<grid, kImportBlock, 0, st>>>(a.g, a.src, a.srcStart, a.srcLeave, a.tag, a.order, a.dirOff, a.dst, a.dstStart, a.stay, a.dstCount,
+	                                                    a.reserveOwnOutbox, a.stopFlag, a.stepIndex, a.zBegin, a.zCount, a.zStride > 0 ? a.zStride : 1, FaceMsg{}, FaceMsg{});
 	if (commit) k_commit_flag<<<1, 1, 0, st>>>(a.stopFlag);
 }
 
 void launch_face_pack(const Geometry& g, const ParticleArrays& src, const int64_t* cellStart, const int* nLeave, const unsigned char* tag,
+                      const unsigned short* order, const int* dirOff,
                       int* faceCnt, const FaceMsg& down, const FaceMsg& up, int* totals, int* stopFlag, int stepIndex, cudaStream_t st) {
 	(void)stepIndex;
 	const int tasks = 2 * g.nx * g.ny;
 	const int grid = (tasks + kFaceWarps - 1) / kFaceWarps;
-	k_face_count<<<grid, kFaceBlock, 0, st>>>(g, cellStart, nLeave, tag, faceCnt, stopFlag);
+	k_face_count<<<grid, kFaceBlock, 0, st>>>(g, cellStart, nLeave, tag, dirOff, faceCnt, stopFlag);
 	k_face_scan<<<2, 1024, 0, st>>>(g, faceCnt, down, up, totals);
-	k_face_copy<<<grid, kFaceBlock, 0, st>>>(g, src, cellStart, nLeave, tag, down, up);
+	k_face_copy<<<grid, kFaceBlock, 0, st>>>(g, src, cellStart, nLeave, tag, order, dirOff, down, up);
 }
 
 void launch_gather_current(const Geometry& g, const double* cellJ, double* J, const int* stopFlag, cudaStream_t st) {

@@ -12,12 +12,16 @@ struct MoveArgs {
 	int* countOut;             // number of stayers per cell (head of the segment in `out`)
 	int* nLeave;
 	unsigned char* tag;
+	unsigned short* order;     // per slot: direction-sorted index of the cell's outbox (sort_outbox), written by the mover
+	int* dirOff;               // per local cell: 28 exclusive prefix counts over the direction codes (-1: no index)
 	const double* fieldEB;     // (n+3)^3 x 6 : E.xyz B.xyz per node (mode "interpolated")
 	double* cellJ;             // cells x 24 corner sums (deposit)
 	const int* stopFlag;
-	int zBegin, zCount;        // owned z-planes [zBegin, zBegin+zCount) of the slab
+	int zBegin, zCount;        // owned z-planes zBegin, zBegin + zStride, ... (zCount of them) of the slab
+	int zStride;               // 0 / 1: consecutive planes; lz - 1 with zCount 2: the slab's two boundary planes in one launch
 	int stages;                // shared-memory tile stages per CTA (TMA ring)
 	bool interpolate, deposit, migrate, push;   // push=false: deposit-only pass (no write-back)
+	bool sortPass;             // follow the mover with k_sort_outbox (worth it when outboxes of more than 32 entries are expected)
 	// chunked mover (several CTAs per cell, k_move_chunk): the chunks [chunkFirst, chunkFirst + chunkCount) of the table
 	bool chunked;
 	const int2* chunkTable;    // per chunk: (local cell id, index of the chunk within the cell)
@@ -33,23 +37,26 @@ int chunk_particles();
 struct ImportArgs {
 	Geometry g;
 	ParticleArrays src; const int64_t* srcStart; const int* srcLeave; const unsigned char* tag;
+	const unsigned short* order; const int* dirOff;   // the movers' direction-sorted outbox index (slots of srcStart's layout)
 	ParticleArrays dst; const int64_t* dstStart; const int* stay; int* dstCount;
 	int reserveOwnOutbox;      // 1 while other cells may still read this cell's outbox out of `dst`
 	int* stopFlag;             // [0] stop, [1] first failing step, [2] overflow seen in this pass
 	int stepIndex;
-	int zBegin, zCount;
+	int zBegin, zCount, zStride;   // planes zBegin, zBegin + zStride, ... (zStride 0 / 1: consecutive)
 	bool slab;                 // z-slab context: neighbours beyond the slab's first / last plane are columns of the face messages
 	FaceMsg fromDown, fromUp;
 };
 
-void launch_move(const MoveArgs& a, cudaStream_t st);
+// returns the number of kernels launched (the mover; after a migrating push also k_sort_outbox, which indexes the outboxes
+// the mover only marked).  stopFlag points at the context's 8 control words: [0] stop ... [4] "an outbox awaits sorting"
+int launch_move(const MoveArgs& a, cudaStream_t st);
 // does launch_move run the warp-specialised kernel (k_move_ws: a fifth warp deposits) for these switches?
 bool move_uses_ws(const Geometry& g, bool deposit, bool interpolate, bool push);
 // `commit`: also raise the stop flag if any import pass of this step overflowed a cell segment
 void launch_import(const ImportArgs& a, bool commit, cudaStream_t st);
 // z-slab exchange: pack both faces of the slab into their messages (3 launches)
 void launch_face_pack(const Geometry& g, const ParticleArrays& src, const int64_t* cellStart, const int* nLeave, const unsigned char* tag,
-                      int* faceCnt, const FaceMsg& down, const FaceMsg& up, int* totals, int* stopFlag, int stepIndex, cudaStream_t st);
+                      const unsigned short* order, const int* dirOff, int* faceCnt, const FaceMsg& down, const FaceMsg& up, int* totals, int* stopFlag, int stepIndex, cudaStream_t st);
 void launch_gather_current(const Geometry& g, const double* cellJ, double* J, const int* stopFlag, cudaStream_t st);
 void launch_count_misplaced(const Geometry& g, const ParticleArrays& p, const int64_t* cellStart, const int* count, unsigned long long* bad, cudaStream_t st);
 void launch_scatter_aos(const Geometry& g, const double* aos, const int64_t* aosStart, const ParticleArrays& p, const int64_t* cellStart, cudaStream_t st);

@@ -511,6 +511,15 @@ def run_b200(args):
         n_local = int(counts.sum())
         host = torch.from_numpy(np.ascontiguousarray(aos)).pin_memory()
         del aos
+    elif args.workload == "medium" and args.device_init:
+        # phase 1 of initCells on the host (sequential by construction, ~2 s), phase 2 on the GPU (ipic_generate_normal_speed)
+        args.no_e2e = True
+        deck = capi.Deck(os.path.join(ROOT, "tests", "golden", "inputs", "medium.inp"))
+        props = capi.Props.from_other(deck.props)
+        counts = deck.counts(rank * lz, lz)
+        n_total = cfg["particles"]
+        n_local = int(counts.sum())
+        host = None
     elif args.workload == "medium":
         # the deck as `ipic3d medium.inp` sets it up; every rank generates ONLY its z-slab (phase 1 of initCells is cheap and
         # replicated, phase 2 is per cell), straight into pinned memory
@@ -539,11 +548,16 @@ def run_b200(args):
         uid = [ipic.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0])
-    if host is None:
+    t_init = time.perf_counter()
+    if host is None and args.workload == "medium":
+        ctx.generate_normal_speed(counts, *deck.distribution())
+        deck.close()
+    elif host is None:
         ctx.generate_uniform(n_total)
     else:
         ctx.upload_cells_ptr(counts, host.data_ptr())
     particle_fields = ctx.particle_fields()
+    t_init = time.perf_counter() - t_init
 
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps -------------------
     sampler = ClockSampler(local)
@@ -660,7 +674,8 @@ def run_b200(args):
                         "" if args.no_deposit else " + current deposit", ", NCCL send/recv of face messages" if world > 1 else ""),
                     "deposit": not args.no_deposit, "parallelism": "zslab%d" % world, "particle_fields_in_hbm": particle_fields,
                     "l2": "inputs (%.2f GB of particle state per GPU) are larger than L2; no flush needed" % (n_local * 64 / 1e9),
-                    "relayouts_since_upload": relayouts},
+                    "relayouts_since_upload": relayouts,
+                    "universe_into_hbm_s": t_init, "universe_source": "device generator" if host is None else "host generator + upload of pinned AoS"},
             "parity_gate": gate,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "particles_alive_before": alive_before, "particles_alive_after": alive, "misplaced_after": misplaced,

@@ -62,6 +62,10 @@ namespace ipic3d {
 
 		Universe createUniverse() const { return createUniverseFromDistribution(properties, init, numParticles, protons()); }
 
+		// the same universe without its particles (grids only): for runs that create the particles on the device
+		// (populateOnDevice in simulator.h) and never need them on the host
+		Universe createUniverseWithoutParticles() const { return detail::assembleUniverse(properties, init, Cells(properties.size)); }
+
 		// The same universe piecewise, for callers that never hold all of it (one z-slab per GPU / per process):
 		// phase 1 of initCells once (cheap, sequential, identical everywhere), then any cell on its own.
 		std::vector<std::uint64_t> cellPopulations() const { return detail::approximatePopulation(properties, (std::uint64_t)numParticles, protons()); }

@@ -444,6 +444,30 @@ namespace ipic3d {
 		out << "\nTotal: " << total << "\n";
 	}
 
+	// Creates the particles of `universe` directly in HBM (resident mode only: inside a ResidentScope): phase 2 of
+	// initCells<uniform_pos_normal_speed> (hdr/cell.h:596-632) on the device(s), from the per-cell populations of phase 1
+	// (z-fastest flatten, e.g. EarthDeck::cellPopulations) and the distribution's velocity parameters.  The host cells stay
+	// empty until syncToHost(universe); simulateSteps finds the universe on the device.  Bit-identical to initCells.
+	inline void populateOnDevice(Universe& universe, const std::vector<std::uint64_t>& population, const Vector3<double>& mean,
+	                             const Vector3<double>& stddev, double q, double qom) {
+		detail::Session& session = detail::Session::instance();
+		if (!session.residentMode()) { std::cerr << "ipic3d_b200: populateOnDevice needs resident mode (a ResidentScope)" << std::endl; std::exit(EXIT_FAILURE); }
+		const UniverseProperties& p = universe.properties;
+		const ipic_props abi = p.toAbi();
+		session.prepare(abi, detail::slabDevices(p.size.z));
+		session.forget();
+		const int gpus = (int)session.ctx.size();
+		const std::int64_t lz = p.size.z / gpus;
+		const double m[3] = { mean.x, mean.y, mean.z }, sd[3] = { stddev.x, stddev.y, stddev.z };
+		std::vector<std::uint64_t> slab((std::size_t)(p.size.x * p.size.y * lz));
+		for (int r = 0; r < gpus; ++r) {
+			for (std::size_t c = 0; c < slab.size(); ++c) slab[c] = population[(c / (std::size_t)lz) * (std::size_t)p.size.z + (std::size_t)(r * lz) + c % (std::size_t)lz];
+			detail::check(ipic_generate_normal_speed(session.ctx[(std::size_t)r], slab.data(), m, sd, q, qom), "ipic_generate_normal_speed");
+		}
+		session.residentOf = &universe;
+		session.hostStale = true;
+	}
+
 	// While an object of this type lives, simulateSteps keeps universes in HBM between calls; at the end of the scope the
 	// host copy of `universe` is brought up to date (unless dismissed: the caller only wanted counts / diagnostics).
 	class ResidentScope {

@@ -158,6 +158,17 @@ IPIC_API void* ipic_host_deck_open(const char* path, ipic_props* props, uint64_t
 
 IPIC_API void ipic_host_deck_close(void* handle) { delete static_cast<DeckHandle*>(handle); }
 
+// what phase 2 of initCells needs besides the populations: the velocity distribution and the species (for the device generator,
+// ipic_generate_normal_speed): mean 0, sigma = the 10 MeV proton's speed per component, q = e, qom = e / m_p (hdr/cell.h:503-504)
+IPIC_API void ipic_host_deck_distribution(void* handle, double* mean3, double* stddev3, double* q, double* qom) {
+	const DeckHandle* h = static_cast<DeckHandle*>(handle);
+	const double v = h->deck.thermalSpeed();
+	const double e = 1.602176565e-19, m = 1.672621777e-27;
+	for (int a = 0; a < 3; ++a) { mean3[a] = 0.0; stddev3[a] = v; }
+	*q = e;
+	*qom = e / m;
+}
+
 // populations of the z-planes [zBegin, zBegin + zCount) in slab order (x*ny + y)*zCount + zl
 IPIC_API int ipic_host_deck_counts(void* handle, int zBegin, int zCount, uint64_t* counts) {
 	const DeckHandle* h = static_cast<DeckHandle*>(handle);

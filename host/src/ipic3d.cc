@@ -26,16 +26,24 @@ namespace {
 		std::cout << "Initializing simulation state ..." << std::endl;
 		const EarthDeck deck(path, baseName);
 		std::cout << deck.init << deck.properties;
-		Universe universe = deck.createUniverse();
+		// The run only reports per-cell counts afterwards, so by default the particles live in HBM from start to end: created
+		// there (phase 1 of initCells on the host, phase 2 on the device, bit-identical), stepped there, counted there.
+		// IPIC3D_RESIDENT=0: the reference's flow -- host universe, upload, steps, download of every particle.
+		const char* residentEnv = std::getenv("IPIC3D_RESIDENT");
+		const bool resident = !(residentEnv && std::atoi(residentEnv) == 0);
+		Universe universe = resident ? deck.createUniverseWithoutParticles() : deck.createUniverse();
+		struct OptionalScope { ResidentScope* s; ~OptionalScope() { delete s; } } scope{ resident ? new ResidentScope(universe) : nullptr };
+		if (resident) {
+			scope.s->dismiss();
+			const double v = deck.thermalSpeed();
+			const double e = 1.602176565e-19, m = 1.672621777e-27;
+			std::cout << "Populating cells ...\n";
+			populateOnDevice(universe, deck.cellPopulations(), Vector3<double>{ 0, 0, 0 }, Vector3<double>{ v, v, v }, e, e / m);
+		}
 
 		std::cout << "Running simulation..." << std::endl;
 		const std::uint64_t cycles = deck.params.ncycles;
 		const int n = deck.numParticles;
-		// the run only reports per-cell counts afterwards: leave the particles in HBM (IPIC3D_RESIDENT=0: download them all)
-		const char* residentEnv = std::getenv("IPIC3D_RESIDENT");
-		const bool resident = !(residentEnv && std::atoi(residentEnv) == 0);
-		struct OptionalScope { ResidentScope* s; ~OptionalScope() { delete s; } } scope{ resident ? new ResidentScope(universe) : nullptr };
-		if (resident) scope.s->dismiss();
 		const DurationMeasurement t = simulateSteps(cycles, universe);
 
 		std::cout << "Simulation measurements: " << n << " initial particles, first step " << t.firstStep << " seconds, " << (n / t.firstStep)

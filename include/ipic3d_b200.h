@@ -131,6 +131,15 @@ IPIC_API int  ipic_upload_cells(ipic_ctx* ctx, const uint64_t* counts, const dou
  * two engine calls per double), electrons (q -1, qom -25).  Bit-identical to the host generator: the LCG is jumped ahead
  * per particle, the floating-point steps are the library's, unfused.  Replaces ipic_upload_cells for this universe. */
 IPIC_API int  ipic_generate_uniform(ipic_ctx* ctx, uint64_t num_particles);
+/* The universe of `ipic3d <deck>` created directly in HBM: phase 2 of initCells<Distribution> (cell.h:596-632) for the context's
+ * cells with the distribution main() builds (ipic3d.cxx:72-83, distribution::uniform_pos_normal_speed): per cell, seed
+ * (x*1023 + y)*1023 + z, positions uniform in the cell's box from std::minstd_rand(seed) (cell.h:138-174), velocity components
+ * mean + stddev * ziggurat sample (cell.h:222-257, ziggurat_normal_distribution.h: 64-bit SHR3 state 123456789 ^ s with
+ * s = the seed after generic_particle_generator::seed's two (1023 s) & s steps, cell.h:281-287), charge q and charge-to-mass
+ * ratio qom for every particle (cell.h:624-625).  counts (owned cells, slab order) are the populations of phase 1, which is
+ * sequential by construction and stays with the caller (host mirror: EarthDeck::cellPopulations).  Bit-identical to the host
+ * generator.  Replaces ipic_upload_cells for such a universe: nothing crosses PCIe but the counts. */
+IPIC_API int  ipic_generate_normal_speed(ipic_ctx* ctx, const uint64_t* counts, const double* mean3, const double* stddev3, double q, double qom);
 IPIC_API int  ipic_download_cells(ipic_ctx* ctx, uint64_t* counts, double* particles_aos, uint64_t capacity_particles);
 IPIC_API int  ipic_cell_counts(ipic_ctx* ctx, uint64_t* counts);
 IPIC_API int  ipic_total_particles(ipic_ctx* ctx, uint64_t* total);

@@ -665,6 +665,30 @@ def test_device_generator_bit_identical(n):
         assert np.array_equal(counts, want_counts) and bits_equal(aos, want)
 
 
+@pytest.mark.parametrize("deck,slabs,one_species", [("test.inp", 1, True), ("test.inp", 2, True), ("test.inp", 1, False), ("tiny.inp", 4, True)])
+def test_device_deck_generator_bit_identical(golden_dir, deck, slabs, one_species):
+    """ipic_generate_normal_speed: phase 2 of initCells<uniform_pos_normal_speed> on the device (minstd jump-ahead for the
+    positions, the ziggurat with glibc's logf restated for the velocities): every particle equals the reference's, bit for bit."""
+    from allscale_ipic3d_b200 import capi
+    import allscale_ipic3d_b200 as ipic
+    if not Ref.available():
+        pytest.skip("oracle/_ref not built")
+    path = os.path.join(golden_dir, "inputs", deck)
+    ref = Ref.from_inp(path)
+    want_counts, want_aos = ref.counts(), ref.particles()
+    with capi.Deck(path) as d:
+        nz = int(d.props.size[2]); nxy = int(d.props.size[0] * d.props.size[1])
+        for rank in range(slabs):
+            with ipic.Context(d.props, device=0, rank=rank, nranks=slabs) as c:
+                c.set_uniform_species(one_species)
+                counts = d.generate_on_device(c, rank, slabs)
+                assert c.particle_fields() == (6 if one_species else 8)
+                got_counts, got = c.download_cells()
+            wc, wa = capi.slab_of(want_counts, want_aos, nxy, nz, rank, slabs)
+            assert np.array_equal(counts, wc) and np.array_equal(got_counts, wc)
+            assert bits_equal(got, wa), "slab %d of %d" % (rank, slabs)
+
+
 @pytest.mark.parametrize("one_species", [True, False])
 def test_fused_deposit_deep_cells(one_species):
     """The warp-specialised mover + deposit (k_move_ws) on cells of ~2500 particles = 20 tiles, i.e. well past the 8-stage
