@@ -1,0 +1,45 @@
+"""The reference's OWN unit-test sources (code/app/test/*.cc), unmodified, compiled against the host mirror (host/include:
+the drop-in data model, parser and simulateSteps) instead of the reference's headers -- the switch a user of the reference
+would make.  The binaries are built where /root/reference exists (oracle/Makefile, target mirrortests) and travel with
+oracle/_ref; nothing here reads /root/reference at run time.
+
+  init / parameters / particle / universe   pure host code: run in the CPU suite
+  simulation (9 cases)                      simulateSteps / simulateStep on universes the tests build and mutate by hand:
+                                            Boris straight line, Larmor 1000 steps, ExB drift 5000 steps, migration and
+                                            reflection on 3^3 and 4^3 grids -- every step runs on the GPU (-m gpu)
+"""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+UT = os.path.join(ROOT, "oracle", "_ref", "ut_mirror")
+
+
+def run_cases(name, timeout=900):
+    exe = os.path.join(UT, name + "_test")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ut_mirror not built (reference sources absent at build time)")
+    out = subprocess.run([exe], cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    text = out.stdout + out.stderr
+    m = re.search(r"(\d+) cases, (\d+) failed", text)
+    assert m, text[-2000:]
+    assert out.returncode == 0 and int(m.group(2)) == 0, text[-3000:]
+    return int(m.group(1)), text
+
+
+@pytest.mark.parametrize("name,cases", [("init", 2), ("parameters", 2), ("particle", 2), ("universe", 7)])
+def test_reference_host_unit_tests_pass_against_the_mirror(name, cases):
+    n, _ = run_cases(name)
+    assert n == cases
+
+
+@pytest.mark.gpu
+def test_reference_simulation_tests_pass_on_the_gpu():
+    """simulation_test.cc: every TEST drives simulateSteps / simulateStep of the mirror, i.e. the CUDA kernels."""
+    n, text = run_cases("simulation")
+    assert n >= 8, text[-2000:]
+    for case in ("SingleParticleBorisMover", "SingleParticleLarmorRadius", "SingleParticleBorisMoverExBdrift", "ParticleMigration"):
+        assert re.search(r"OK \] Simulation\.%s" % case, text), case
