@@ -23,6 +23,7 @@ API_SYMBOLS = [
     "ipic_set_exchange_capacity", "ipic_group_create", "ipic_group_step", "ipic_relayout_count",
     "ipic_alloc_pinned", "ipic_free_pinned", "ipic_set_uniform_species", "ipic_particle_fields", "ipic_profile_phases",
     "ipic_diagnostics", "ipic_group_diagnostics", "ipic_trace", "ipic_generate_uniform", "ipic_generate_normal_speed",
+    "ipic_create_slab_range", "ipic_group_create_ranges",
 ]
 
 
@@ -102,17 +103,22 @@ def _up(a):
 class Context:
     """One z-slab of a universe on one GPU (``ipic_ctx``).  Single GPU: rank 0 of 1."""
 
-    def __init__(self, props, device=0, rank=0, nranks=1, _handle=None):
+    def __init__(self, props, device=0, rank=0, nranks=1, _handle=None, z_begin=None, z_count=None):
+        """z_begin / z_count: the slab's planes when the slabs are not equally thick (ipic_create_slab_range)."""
         self.lib = load_library()
         self.props = Props.from_other(props)
         self.rank, self.nranks = rank, nranks
         self.h = C.c_void_p()
+        if z_count is None:
+            z_count = int(self.props.size[2]) // nranks
+            z_begin = rank * z_count
+        self.z_begin, self.z_count = int(z_begin), int(z_count)
         if _handle is not None:
             self.h = C.c_void_p(_handle)
         else:
-            self._ck(self.lib.ipic_create_slab(C.byref(self.props), C.c_int(device), C.c_int(rank), C.c_int(nranks), C.byref(self.h)))
-        nz = int(self.props.size[2]) // nranks
-        self.owned_cells = int(self.props.size[0] * self.props.size[1]) * nz
+            self._ck(self.lib.ipic_create_slab_range(C.byref(self.props), C.c_int(device), C.c_int(rank), C.c_int(nranks),
+                                                     C.c_int(self.z_begin), C.c_int(self.z_count), C.byref(self.h)))
+        self.owned_cells = int(self.props.size[0] * self.props.size[1]) * self.z_count
 
     def _ck(self, rc):
         if rc != 0:
@@ -268,21 +274,25 @@ class Group:
     """All z-slabs of a universe in ONE process (``ipic_group_create``): rank r on ``devices[r]`` (devices may
     repeat), exchange by peer copies.  Host arrays are given / returned for the whole universe."""
 
-    def __init__(self, props, devices):
+    def __init__(self, props, devices, planes=None):
+        """planes: number of z-planes per slab (default: equal slabs)."""
         self.lib = load_library()
         self.props = Props.from_other(props)
         n = len(devices)
         self.nz = int(self.props.size[2])
-        if self.nz % n:
-            raise ValueError("nz=%d is not divisible by %d slabs" % (self.nz, n))
-        self.lz = self.nz // n
+        if planes is None:
+            if self.nz % n:
+                raise ValueError("nz=%d is not divisible by %d slabs" % (self.nz, n))
+            planes = [self.nz // n] * n
+        self.planes = [int(p) for p in planes]
+        self.z0 = [int(sum(self.planes[:r])) for r in range(n)]
         handles = (C.c_void_p * n)()
         devs = (C.c_int * n)(*devices)
-        rc = self.lib.ipic_group_create(C.byref(self.props), devs, C.c_int(n), handles)
+        rc = self.lib.ipic_group_create_ranges(C.byref(self.props), devs, C.c_int(n), (C.c_int * n)(*self.z0), (C.c_int * n)(*self.planes), handles)
         if rc:
             raise IpicError(rc, self.lib.ipic_last_error().decode())
         self._handles = handles
-        self.members = [Context(self.props, devices[r], r, n, _handle=handles[r]) for r in range(n)]
+        self.members = [Context(self.props, devices[r], r, n, _handle=handles[r], z_begin=self.z0[r], z_count=self.planes[r]) for r in range(n)]
 
     def close(self):
         for m in self.members:
@@ -298,7 +308,7 @@ class Group:
     def _slab_index(self, r):
         """Indices of rank r's cells in the global flatten, in slab order (x*ny + y)*lz + zl."""
         nxy = int(self.props.size[0] * self.props.size[1])
-        return (np.arange(nxy)[:, None] * self.nz + r * self.lz + np.arange(self.lz)[None, :]).reshape(-1)
+        return (np.arange(nxy)[:, None] * self.nz + self.z0[r] + np.arange(self.planes[r])[None, :]).reshape(-1)
 
     def upload_cells(self, counts, aos):
         counts = np.ascontiguousarray(counts, dtype=np.uint64)
@@ -446,13 +456,37 @@ def uniform_universe(props, num_particles, z_begin=0, z_count=None, threads=0):
     return counts, aos
 
 
-def slab_of(counts, aos, nxy, nz, rank, world):
-    """The z-slab `rank` of `world` of a universe given as per-cell counts (z-fastest flatten) + cell-major AoS particles:
-    (counts, particles) of the slab's cells in slab order (x*ny + y)*lz + zl."""
+def balanced_planes(plane_load, world):
+    """Cuts nz z-planes into `world` consecutive slabs of about equal load (e.g. particles per plane), at least one plane
+    each: the list of planes per slab.  Greedy on the cumulative load: slab r ends where the running sum first reaches
+    (r + 1) / world of the total, leaving enough planes for the slabs that follow."""
+    load = np.asarray(plane_load, dtype=np.float64)
+    nz = len(load)
+    if world > nz:
+        raise ValueError("%d slabs need at least as many z-planes (%d)" % (world, nz))
+    cum = np.concatenate([[0.0], np.cumsum(load)])
+    cuts = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        z = int(np.searchsorted(cum, target, side="left"))
+        # the cut that leaves the smaller imbalance, within what the remaining slabs allow
+        if z > 0 and abs(cum[z - 1] - target) <= abs(cum[min(z, nz)] - target):
+            z -= 1
+        z = max(z, cuts[-1] + 1)
+        z = min(z, nz - (world - r))
+        cuts.append(z)
+    cuts.append(nz)
+    return [cuts[r + 1] - cuts[r] for r in range(world)]
+
+
+def slab_of(counts, aos, nxy, nz, rank, world, z_begin=None, z_count=None):
+    """The z-slab `rank` of `world` (or the planes [z_begin, z_begin + z_count)) of a universe given as per-cell counts
+    (z-fastest flatten) + cell-major AoS particles: (counts, particles) of the slab's cells in slab order (x*ny + y)*lz + zl."""
     counts = np.asarray(counts)
-    lz = nz // world
+    lz = nz // world if z_count is None else z_count
+    z0 = rank * lz if z_begin is None else z_begin
     first = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-    cells = (np.arange(nxy)[:, None] * nz + rank * lz + np.arange(lz)[None, :]).reshape(-1)
+    cells = (np.arange(nxy)[:, None] * nz + z0 + np.arange(lz)[None, :]).reshape(-1)
     mine = counts[cells]
     offset = np.concatenate([[0], np.cumsum(mine)[:-1]]).astype(np.int64)
     idx = np.repeat(first[cells] - offset, mine.astype(np.int64)) + np.arange(int(mine.sum()))
@@ -496,6 +530,11 @@ class Deck:
         if self.lib.ipic_host_deck_particles(self.h, C.c_int(z_begin), C.c_int(z_count), C.c_void_p(aos_ptr), C.c_int(threads)):
             raise IpicError(-1, "ipic_host_deck_particles: bad arguments")
 
+    def plane_population(self):
+        """particles per z-plane of the whole universe (what balanced_planes cuts by)"""
+        nz = int(self.props.size[2])
+        return self.counts(0, nz).reshape(-1, nz).sum(axis=0)
+
     def distribution(self):
         """(mean[3], stddev[3], q, qom) of phase 2: what ipic_generate_normal_speed needs besides the populations."""
         m, s = (C.c_double * 3)(), (C.c_double * 3)()
@@ -504,9 +543,8 @@ class Deck:
         return list(m), list(s), q.value, qom.value
 
     def generate_on_device(self, ctx, rank=0, world=1):
-        """z-slab `rank` of `world` created in the context's HBM (phase 1 populations from the host, phase 2 on the GPU)."""
-        lz = int(self.props.size[2]) // world
-        counts = self.counts(rank * lz, lz)
+        """the context's z-slab created in its HBM (phase 1 populations from the host, phase 2 on the GPU)."""
+        counts = self.counts(ctx.z_begin, ctx.z_count)
         ctx.generate_normal_speed(counts, *self.distribution())
         return counts
 
@@ -520,14 +558,18 @@ class Deck:
         return counts, aos
 
 
-def deck_slab_pinned(deck_path, rank, world, torch):
-    """z-slab `rank` of `world` of the deck's universe generated straight into pinned host memory: (props, counts, tensor)."""
+def deck_slab_pinned(deck_path, rank, world, torch, balanced=False):
+    """z-slab `rank` of `world` of the deck's universe generated straight into pinned host memory:
+    (props, counts, tensor, (z_begin, z_count)).  balanced: slabs cut by particle count instead of equally thick."""
     with Deck(deck_path) as d:
-        lz = int(d.props.size[2]) // world
-        counts = d.counts(rank * lz, lz)
-        host = torch.empty((int(counts.sum()), 8), dtype=torch.float64).pin_memory()
-        d.particles_into(host.data_ptr(), rank * lz, lz)
-        return Props.from_other(d.props), counts, host
+        nz = int(d.props.size[2])
+        planes = balanced_planes(d.plane_population(), world) if balanced else [nz // world] * world
+        z0, lz = int(sum(planes[:rank])), planes[rank]
+        counts = d.counts(z0, lz)
+        host = torch.empty((max(int(counts.sum()), 1), 8), dtype=torch.float64).pin_memory()
+        if counts.sum():
+            d.particles_into(host.data_ptr(), z0, lz)
+        return Props.from_other(d.props), counts, host[:int(counts.sum())], (z0, lz)
 
 
 def dipole_universe(deck_path, grid, per_dim):

@@ -46,6 +46,8 @@ struct ipic_group;
 
 struct ipic_ctx {
 	int device = 0, rank = 0, nranks = 1;
+	int zBegin = 0, zCount = 0;                    // the slab's z-planes [zBegin, zBegin + zCount) of the global grid
+	std::vector<int> slabZ0, slabLz;               // every rank's planes (known after the negotiation before the first step)
 	ipic_props props{};
 	Geometry g{};
 	cudaStream_t stream = nullptr;
@@ -234,8 +236,8 @@ void fillGeometry(ipic_ctx* c) {
 	const ipic_props& p = c->props;
 	Geometry& g = c->g;
 	g.nx = (int)p.size[0]; g.ny = (int)p.size[1]; g.nz = (int)p.size[2];
-	g.lz = g.nz / c->nranks;
-	g.z0 = c->rank * g.lz;
+	g.lz = c->zCount > 0 ? c->zCount : g.nz / c->nranks;
+	g.z0 = c->zCount > 0 ? c->zBegin : c->rank * g.lz;
 	g.ncellsLocal = g.nx * g.ny * g.lz;
 	for (int a = 0; a < 3; a++) {
 		g.w[a] = p.cellWidth[a];
@@ -417,11 +419,20 @@ int ipic_free_pinned(void* p) {
 int ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, ipic_ctx** out) {
 	if (!props || !out) return fail(IPIC_ERR_ARG, "null argument");
 	if (nranks < 1 || rank < 0 || rank >= nranks) return fail(IPIC_ERR_ARG, "bad rank %d of %d", rank, nranks);
+	if (props->size[2] % nranks != 0) return fail(IPIC_ERR_ARG, "nz=%lld is not divisible by %d slabs", (long long)props->size[2], nranks);
+	const int lz = (int)(props->size[2] / nranks);
+	return ipic_create_slab_range(props, device, rank, nranks, rank * lz, lz, out);
+}
+
+int ipic_create_slab_range(const ipic_props* props, int device, int rank, int nranks, int zBegin, int zCount, ipic_ctx** out) {
+	if (!props || !out) return fail(IPIC_ERR_ARG, "null argument");
+	if (nranks < 1 || rank < 0 || rank >= nranks) return fail(IPIC_ERR_ARG, "bad rank %d of %d", rank, nranks);
+	if (zBegin < 0 || zCount < 1 || zBegin + zCount > props->size[2]) return fail(IPIC_ERR_ARG, "bad z-range [%d, %d) of %lld planes", zBegin, zBegin + zCount, (long long)props->size[2]);
+	if (nranks == 1 && (zBegin != 0 || zCount != props->size[2])) return fail(IPIC_ERR_ARG, "a single context holds all z-planes");
 	for (int a = 0; a < 3; a++) {
 		if (props->size[a] <= 0 || props->size[a] > (1 << 20)) return fail(IPIC_ERR_ARG, "bad grid size");
 		if (!(props->cellWidth[a] > 0)) return fail(IPIC_ERR_ARG, "cell width must be positive");
 	}
-	if (props->size[2] % nranks != 0) return fail(IPIC_ERR_ARG, "nz=%lld is not divisible by %d slabs", (long long)props->size[2], nranks);
 	if (!(props->dt > 0) || !(props->speedOfLight > 0) || !(props->planetRadius >= 0)) return fail(IPIC_ERR_ARG, "dt, speedOfLight must be positive and planetRadius non-negative");
 	int ndev = 0;
 	CK(cudaGetDeviceCount(&ndev));
@@ -431,6 +442,7 @@ int ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, 
 	struct Guard { ipic_ctx* c; ~Guard() { if (c) ipic_destroy(c); } } guard{ new ipic_ctx() };
 	ipic_ctx* c = guard.c;
 	c->device = device; c->rank = rank; c->nranks = nranks; c->props = *props;
+	c->zBegin = zBegin; c->zCount = zCount;
 	fillGeometry(c);
 	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	const Geometry& g = c->g;
@@ -563,6 +575,20 @@ int establishLayout(ipic_ctx* c, const std::vector<int64_t>& need, int nf, doubl
 	}
 	std::vector<int64_t> start;
 	buildLayout(c, need, start);
+	if (!c->userHeadroom && c->padFloor > 0) {
+		// the adaptive floor must fit the GPU: two generations of nf doubles, a tag byte and an order entry per slot; what is
+		// allocated now would be freed first.  (large.inp on 8 GPUs: 885 M particles per slab, a floor of 1.25 x the mean
+		// population on 512 k cells would ask for 190 GB.)  The floor shrinks until 85 % of the memory suffices.
+		size_t freeB = 0, totalB = 0;
+		if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+			const double perSlot = 2.0 * nf * sizeof(double) + 1 + sizeof(unsigned short);
+			const double have = 0.85 * ((double)freeB + (double)c->slots * (2.0 * c->slotsNf * sizeof(double) + 3));
+			while (c->padFloor > 64 && (double)start.back() * perSlot > have) {
+				c->padFloor /= 2;
+				buildLayout(c, need, start);
+			}
+		}
+	}
 	if (start.back() > c->slots || start.back() < c->slots / 2 || c->slotsNf != nf) {
 		freeParticleBuffers(c);
 		int rc = allocParticleBuffers(c->buf, &c->dTag, &c->dOrder, start.back(), nf);
@@ -799,7 +825,12 @@ struct StepFlags {
 		// field phase runs after it with identical results; the interpolating mover needs the new fields
 		// first, so its projection is a separate read-only pass.
 		fuseDeposit = project && !interp;
+		// Who needs the current where?  A field solver runs replicated on every slab (its in-place node order is global) and
+		// needs J everywhere: the slabs all-gather their per-cell corner sums.  Without a solver every slab only builds J on
+		// its own node planes, for which it needs ONE plane of corner sums from each z-neighbour (a halo exchange).
+		jHalo = project && !solve;
 	}
+	bool jHalo;
 };
 
 MoveArgs moveArgs(ipic_ctx* c, const StepFlags& f, int zBegin, int zCount, int zStride = 1) {
@@ -957,19 +988,30 @@ int allocExchange(ipic_ctx* c, int64_t cap) {
 
 // What a slab contributes to the negotiation before the first step after an upload: its species state
 // (0 = no particles, 6 = one species with the (q, qom) bits that follow, 8 = mixed).
-struct SlabOffer { int64_t species, qBits, qomBits, pad; };
+struct SlabOffer { int64_t species, qBits, qomBits, zRange; };       // zRange = z0 << 32 | lz
 
 SlabOffer offerOf(const ipic_ctx* c) {
 	SlabOffer o{};
 	o.species = c->emptyUpload ? 0 : c->g.nf;
 	std::memcpy(&o.qBits, &c->g.uq, 8);
 	std::memcpy(&o.qomBits, &c->g.uqom, 8);
+	o.zRange = ((int64_t)c->g.z0 << 32) | (int64_t)c->g.lz;
 	return o;
 }
 
 // All slabs use the same particle layout: 6 fields only if every slab that holds particles holds the same single
 // species (arrivals from a neighbour must fit the layout); empty slabs adopt it; otherwise everybody widens to 8.
 int agreeOnLayout(ipic_ctx* c, const std::vector<SlabOffer>& all) {
+	// the slabs must tile the z-axis in rank order
+	c->slabZ0.clear(); c->slabLz.clear();
+	int next = 0;
+	for (const SlabOffer& o : all) {
+		const int z0 = (int)(o.zRange >> 32), lz = (int)(o.zRange & 0xffffffff);
+		if (z0 != next || lz < 1) return fail(IPIC_ERR_ARG, "the slabs do not tile the z-axis in rank order (slab %d starts at plane %d, expected %d)", (int)c->slabZ0.size(), z0, next);
+		c->slabZ0.push_back(z0); c->slabLz.push_back(lz);
+		next = z0 + lz;
+	}
+	if (next != c->g.nz) return fail(IPIC_ERR_ARG, "the slabs cover %d of %d z-planes", next, c->g.nz);
 	bool uniform = true, any = false;
 	int64_t q = 0, m = 0;
 	for (const SlabOffer& o : all) {
@@ -1026,19 +1068,21 @@ ipic_ctx* neighbour(const ipic_ctx* c, int dir) {      // in-process group only
 
 // every rank ends up with the corner sums of all cells (slab r is the r-th contiguous piece of dCellJ)
 int allGatherCellJ(ipic_ctx* c) {
-	const size_t slabDoubles = (size_t)c->g.nx * c->g.ny * c->g.lz * 24;
+	const size_t planeBytes = (size_t)c->g.nx * c->g.ny * 24 * sizeof(double);      // cellJ is z-major: a slab is one contiguous piece
 	CK(cudaStreamWaitEvent(c->commStream, c->evMoved, 0));
 	CK(cudaStreamWaitEvent(c->commStream, c->evPacked, 0));
 	if (c->comm) {
-		int rc = comm_allgather(c->comm, c->dCellJ + (size_t)c->rank * slabDoubles, c->dCellJ, slabDoubles * sizeof(double), c->commStream, g_lastError);
+		std::vector<size_t> off((size_t)c->nranks), len((size_t)c->nranks);
+		for (int r = 0; r < c->nranks; r++) { off[(size_t)r] = (size_t)c->slabZ0[(size_t)r] * planeBytes; len[(size_t)r] = (size_t)c->slabLz[(size_t)r] * planeBytes; }
+		int rc = comm_allgatherv(c->comm, c->dCellJ, off.data(), len.data(), c->commStream, g_lastError);
 		if (rc) return rc;
 	} else {
 		for (ipic_ctx* m : c->group->members) {
 			if (m == c) continue;
 			CK(cudaStreamWaitEvent(c->commStream, m->evMoved, 0));
 			CK(cudaStreamWaitEvent(c->commStream, m->evPacked, 0));
-			CK(cudaMemcpyPeerAsync(c->dCellJ + (size_t)m->rank * slabDoubles, c->device, m->dCellJ + (size_t)m->rank * slabDoubles, m->device,
-			                       slabDoubles * sizeof(double), c->commStream));
+			const size_t offD = (size_t)m->g.z0 * planeBytes / sizeof(double);
+			CK(cudaMemcpyPeerAsync(c->dCellJ + offD, c->device, m->dCellJ + offD, m->device, (size_t)m->g.lz * planeBytes, c->commStream));
 		}
 	}
 	CK(cudaEventRecord(c->evJ, c->commStream));
@@ -1046,10 +1090,40 @@ int allGatherCellJ(ipic_ctx* c) {
 }
 
 // main stream: wait for the all-gather, then the node-centric gather of J
-int finishCurrent(ipic_ctx* c) {
+int finishCurrent(ipic_ctx* c, bool ownPlanesOnly = false) {
 	CK(cudaStreamWaitEvent(c->stream, c->evJ, 0));
-	launch_gather_current(c->g, c->dCellJ, c->dJ, c->dStop, c->stream);
+	if (ownPlanesOnly) launch_gather_current(c->g, c->dCellJ, c->dJ, c->dStop, c->stream, c->g.z0, c->g.lz + 1);
+	else launch_gather_current(c->g, c->dCellJ, c->dJ, c->dStop, c->stream);
 	c->launches++;
+	return IPIC_OK;
+}
+
+// Halo of the current projection: the corner sums of my lowest / highest cell plane go to the slab below / above, theirs
+// arrive at the places of the planes just outside my slab in the (global-sized) cellJ array -- everything the node planes
+// z0 .. z0 + lz need (projectToDensityField reaches one cell down, periodically, hdr/cell.h:797-806).  The boundary planes'
+// sums are complete once the boundary movers are done, so this runs under the interior mover.
+int exchangeCellJHalo(ipic_ctx* c) {
+	const Geometry& g = c->g;
+	const size_t planeDoubles = (size_t)g.nx * g.ny * 24;
+	double* myLow = c->dCellJ + (size_t)g.z0 * planeDoubles;
+	double* myHigh = c->dCellJ + (size_t)(g.z0 + g.lz - 1) * planeDoubles;
+	double* fromBelow = c->dCellJ + (size_t)((g.z0 - 1 + g.nz) % g.nz) * planeDoubles;
+	double* fromAbove = c->dCellJ + (size_t)((g.z0 + g.lz) % g.nz) * planeDoubles;
+	CK(cudaStreamWaitEvent(c->commStream, c->evPacked, 0));
+	if (c->comm) {
+		CommPiece sends[2] = { { myHigh, planeDoubles * sizeof(double), +1 }, { myLow, planeDoubles * sizeof(double), -1 } };
+		CommPiece recvs[2] = { { fromBelow, planeDoubles * sizeof(double), -1 }, { fromAbove, planeDoubles * sizeof(double), +1 } };
+		int rc = comm_sendrecv(c->comm, sends, 2, recvs, 2, c->commStream, g_lastError);
+		if (rc) return rc;
+	} else {
+		ipic_ctx* down = neighbour(c, -1);
+		ipic_ctx* up = neighbour(c, +1);
+		CK(cudaStreamWaitEvent(c->commStream, down->evPacked, 0));
+		CK(cudaStreamWaitEvent(c->commStream, up->evPacked, 0));
+		CK(cudaMemcpyPeerAsync(fromBelow, c->device, down->dCellJ + (size_t)(down->g.z0 + down->g.lz - 1) * planeDoubles, down->device, planeDoubles * sizeof(double), c->commStream));
+		CK(cudaMemcpyPeerAsync(fromAbove, c->device, up->dCellJ + (size_t)up->g.z0 * planeDoubles, up->device, planeDoubles * sizeof(double), c->commStream));
+	}
+	CK(cudaEventRecord(c->evJ, c->commStream));
 	return IPIC_OK;
 }
 
@@ -1093,8 +1167,9 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 		break;
 	case PH_PRE_GATHER_J:
 		if (!(f.project && f.interp)) break;
-		{ int rc = allGatherCellJ(c); if (rc) return rc; }
-		{ int rc = finishCurrent(c); if (rc) return rc; }
+		if (f.jHalo) { int rc = exchangeCellJHalo(c); if (rc) return rc; }
+		else { int rc = allGatherCellJ(c); if (rc) return rc; }
+		{ int rc = finishCurrent(c, f.jHalo); if (rc) return rc; }
 		break;
 	case PH_BOUNDARY: {
 		if (!f.fuseDeposit) fieldPhase(c, f);
@@ -1152,7 +1227,8 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 	}
 	case PH_GATHER_J:
 		if (!f.fuseDeposit) break;
-		{ int rc = allGatherCellJ(c); if (rc) return rc; }      // on the comm stream, under the imports
+		if (f.jHalo) { int rc = exchangeCellJHalo(c); if (rc) return rc; }      // two planes, on the comm stream under the interior mover
+		else { int rc = allGatherCellJ(c); if (rc) return rc; }                 // everything, under the imports
 		break;
 	case PH_IMPORT:
 		CK(cudaStreamWaitEvent(c->stream, c->evPacked, 0));   // the boundary planes' movers
@@ -1179,7 +1255,7 @@ int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
 		if (!f.fuseDeposit) break;
 		{
 			ProfSpan wait(c, 3);
-			int rc = finishCurrent(c);
+			int rc = finishCurrent(c, f.jHalo);
 			if (rc) return rc;
 			fieldPhase(c, f);
 		}
@@ -1300,7 +1376,7 @@ int runSlabSteps(ipic_ctx** ctxs, int n, uint64_t numSteps, uint32_t flags, doub
 				// PH_FIELDS of the failed step was queued behind its import and did nothing (every kernel returns on the stop
 				// flag): the all-gathered corner sums of that step are still in dCellJ (the next step's movers, which would
 				// overwrite them, were skipped as well), so build J and advance the fields now, before those movers run again
-				rc = finishCurrent(ctxs[r]); if (rc) return rc;
+				rc = finishCurrent(ctxs[r], f.jHalo); if (rc) return rc;
 				fieldPhase(ctxs[r], f);
 			}
 			// the launches of the current step that were queued behind the failure did nothing: queue them again
@@ -1485,11 +1561,20 @@ int ipic_step(ipic_ctx* c, uint64_t numSteps, uint32_t flags, double* tFirst, do
 }
 
 int ipic_group_create(const ipic_props* props, const int* devices, int ndev, ipic_ctx** out) {
-	if (!props || !devices || !out || ndev < 1) return fail(IPIC_ERR_ARG, "bad group arguments");
+	if (!props || ndev < 1) return fail(IPIC_ERR_ARG, "bad group arguments");
+	if (props->size[2] % ndev != 0) return fail(IPIC_ERR_ARG, "nz=%lld is not divisible by %d slabs", (long long)props->size[2], ndev);
+	const int lz = (int)(props->size[2] / ndev);
+	std::vector<int> z0((size_t)ndev), n((size_t)ndev, lz);
+	for (int r = 0; r < ndev; r++) z0[(size_t)r] = r * lz;
+	return ipic_group_create_ranges(props, devices, ndev, z0.data(), n.data(), out);
+}
+
+int ipic_group_create_ranges(const ipic_props* props, const int* devices, int ndev, const int* zBegin, const int* zCount, ipic_ctx** out) {
+	if (!props || !devices || !out || ndev < 1 || !zBegin || !zCount) return fail(IPIC_ERR_ARG, "bad group arguments");
 	auto grp = std::make_shared<ipic_group>();
 	for (int r = 0; r < ndev; r++) {
 		ipic_ctx* c = nullptr;
-		int rc = ipic_create_slab(props, devices[r], r, ndev, &c);
+		int rc = ipic_create_slab_range(props, devices[r], r, ndev, zBegin[r], zCount[r], &c);
 		if (rc) { for (ipic_ctx* m : grp->members) { m->group.reset(); ipic_destroy(m); } return rc; }
 		grp->members.push_back(c);
 	}

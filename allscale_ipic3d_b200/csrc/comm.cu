@@ -23,6 +23,7 @@ struct NcclApi {
 	int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	int (*GroupStart)() = nullptr;
 	int (*GroupEnd)() = nullptr;
 	const char* (*GetErrorString)(int) = nullptr;
@@ -39,7 +40,7 @@ NcclApi* api(std::string& err) {
 	if (!a.handle) { err = std::string("cannot load NCCL: ") + dlerror(); return nullptr; }
 #define SYM(field, name) a.field = (decltype(a.field))dlsym(a.handle, name); if (!a.field) { err = "NCCL symbol missing: " name; a.handle = nullptr; return nullptr; }
 	SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
-	SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllGather, "ncclAllGather") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
+	SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllGather, "ncclAllGather") SYM(Broadcast, "ncclBroadcast") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
 	SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
 	return &a;
@@ -96,5 +97,18 @@ int comm_allgather(ipic_comm* c, const void* send, void* recv, size_t bytesPerRa
 	NcclApi* a = api(err);
 	if (!a || !c) { if (a) err = "no communicator"; return IPIC_ERR_COMM; }
 	NC(a->AllGather(send, recv, bytesPerRank, ncclInt8, c->comm, st));
+	return IPIC_OK;
+}
+
+int comm_allgatherv(ipic_comm* c, void* base, const size_t* offsets, const size_t* bytes, cudaStream_t st, std::string& err) {
+	NcclApi* a = api(err);
+	if (!a || !c) { if (a) err = "no communicator"; return IPIC_ERR_COMM; }
+	NC(a->GroupStart());
+	for (int r = 0; r < c->nranks; r++) {
+		if (!bytes[r]) continue;
+		char* piece = static_cast<char*>(base) + offsets[r];
+		NC(a->Broadcast(piece, piece, bytes[r], ncclInt8, r, c->comm, st));
+	}
+	NC(a->GroupEnd());
 	return IPIC_OK;
 }

@@ -18,3 +18,5 @@ struct CommPiece { void* p; size_t bytes; int dir; };
 int comm_sendrecv(ipic_comm* c, const CommPiece* sends, int nSends, const CommPiece* recvs, int nRecvs, cudaStream_t st, std::string& err);
 // all-gather equally sized pieces in rank order
 int comm_allgather(ipic_comm* c, const void* send, void* recv, size_t bytesPerRank, cudaStream_t st, std::string& err);
+// all-gather pieces of different sizes in place: rank r's piece is bytes[r] at base + offsets[r] (one broadcast per rank, one NCCL group)
+int comm_allgatherv(ipic_comm* c, void* base, const size_t* offsets, const size_t* bytes, cudaStream_t st, std::string& err);

@@ -101,8 +101,10 @@ __device__ __forceinline__ void sort_outbox_small(const unsigned char* sTags, in
 		// apiece -- measured +0.28 ms on the dipole deck -- so it is written only by the few CTAs that still read it as 0)
 		// sortFlag[0]: this step's k_sort_outbox has work (reset by k_commit_flag); sortFlag[1]: sticky, for the host's decision
 		// whether to launch k_sort_outbox at all in the following steps (ipic_ctx::sortLikely)
+		// (all 28 words are marked: the import looks at the word of ITS direction, and must not take a stale prefix for an index
+		// when the sort pass is skipped)
+		if (lane < 28) dirOff[lane] = kSortPending;
 		if (lane == 0) {
-			dirOff[0] = kSortPending;
 			if (*(volatile int*)sortFlag == 0) *sortFlag = 1;
 			if (*(volatile int*)(sortFlag + 1) == 0) sortFlag[1] = 1;
 		}
@@ -1236,14 +1238,17 @@ k_face_copy(const Geometry g, const ParticleArrays src, const int64_t* __restric
 
 // ---- node-centric gather of the per-cell corner sums (reference cell.h:787-824) -------------------
 
-__global__ void k_gather_current(const Geometry g, const double* __restrict__ cellJ, double* __restrict__ J, const int* __restrict__ stopFlag) {
+// node planes [zNode0, zNode0 + zNodes) of the global (nz + 1)-plane node grid
+__global__ void k_gather_current(const Geometry g, const double* __restrict__ cellJ, double* __restrict__ J, const int* __restrict__ stopFlag,
+                                 int zNode0, int zNodes) {
 	if (*stopFlag) return;
-	const int64_t nn = (int64_t)(g.nx + 1) * (g.ny + 1) * (g.nz + 1);
-	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= nn * 3) return;
-	const int comp = (int)(t % 3);
-	const int64_t node = t / 3;
-	const int z = (int)(node % (g.nz + 1)), y = (int)((node / (g.nz + 1)) % (g.ny + 1)), x = (int)(node / ((int64_t)(g.nz + 1) * (g.ny + 1)));
+	const int64_t nn = (int64_t)(g.nx + 1) * (g.ny + 1) * zNodes;
+	const int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (tt >= nn * 3) return;
+	const int comp = (int)(tt % 3);
+	const int64_t sub = tt / 3;
+	const int z = zNode0 + (int)(sub % zNodes), y = (int)((sub / zNodes) % (g.ny + 1)), x = (int)(sub / ((int64_t)zNodes * (g.ny + 1)));
+	const int64_t t = ((((int64_t)x * (g.ny + 1) + y) * (g.nz + 1)) + z) * 3 + comp;
 	double Js = 0.0;
 	for (int i = -1; i < 1; i++) for (int j = -1; j < 1; j++) for (int k = -1; k < 1; k++) {
 		int ux = x + i, uy = y + j, uz = z + k;
@@ -1510,9 +1515,10 @@ void launch_face_pack(const Geometry& g, const ParticleArrays& src, const int64_
 	k_face_copy<<<grid, kFaceBlock, 0, st>>>(g, src, cellStart, nLeave, tag, order, dirOff, down, up);
 }
 
-void launch_gather_current(const Geometry& g, const double* cellJ, double* J, const int* stopFlag, cudaStream_t st) {
-	const int64_t n = (int64_t)(g.nx + 1) * (g.ny + 1) * (g.nz + 1) * 3;
-	k_gather_current<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, cellJ, J, stopFlag);
+void launch_gather_current(const Geometry& g, const double* cellJ, double* J, const int* stopFlag, cudaStream_t st, int zNode0, int zNodes) {
+	if (zNodes < 0) { zNode0 = 0; zNodes = g.nz + 1; }
+	const int64_t n = (int64_t)(g.nx + 1) * (g.ny + 1) * zNodes * 3;
+	k_gather_current<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, cellJ, J, stopFlag, zNode0, zNodes);
 }
 
 void launch_count_misplaced(const Geometry& g, const ParticleArrays& p, const int64_t* cellStart, const int* count, unsigned long long* bad, cudaStream_t st) {

@@ -57,7 +57,8 @@ void launch_import(const ImportArgs& a, bool commit, cudaStream_t st);
 // z-slab exchange: pack both faces of the slab into their messages (3 launches)
 void launch_face_pack(const Geometry& g, const ParticleArrays& src, const int64_t* cellStart, const int* nLeave, const unsigned char* tag,
                       const unsigned short* order, const int* dirOff, int* faceCnt, const FaceMsg& down, const FaceMsg& up, int* totals, int* stopFlag, int stepIndex, cudaStream_t st);
-void launch_gather_current(const Geometry& g, const double* cellJ, double* J, const int* stopFlag, cudaStream_t st);
+// J on the node planes [zNode0, zNode0 + zNodes) (default: all nz + 1 planes) from the per-cell corner sums
+void launch_gather_current(const Geometry& g, const double* cellJ, double* J, const int* stopFlag, cudaStream_t st, int zNode0 = 0, int zNodes = -1);
 void launch_count_misplaced(const Geometry& g, const ParticleArrays& p, const int64_t* cellStart, const int* count, unsigned long long* bad, cudaStream_t st);
 void launch_scatter_aos(const Geometry& g, const double* aos, const int64_t* aosStart, const ParticleArrays& p, const int64_t* cellStart, cudaStream_t st);
 void launch_gather_aos(const Geometry& g, double* aos, const int64_t* aosStart, const ParticleArrays& p, const int64_t* cellStart, cudaStream_t st);

@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--particles-per-gpu", type=int, default=32_000_000)
     ap.add_argument("--grid", type=int, default=32)
     ap.add_argument("--no-deposit", action="store_true", help="time the loop as the reference ships it (STEP 1 off)")
-    ap.add_argument("--workload", default="uniform", choices=["uniform", "dipole", "medium"],
+    ap.add_argument("--workload", default="uniform", choices=["uniform", "dipole", "medium", "large"],
                     help="uniform = the headline :U:N plasma; dipole = a secondary data point (fixed total, z-slabs over the ranks): the reference's Earth-dipole "
                          ".inp set-up (medium.inp physics: 0.625 R_E cells, 10 MeV protons, absorption, ~17 %% migration per step) on --grid^3 "
                          "cells with 8^3 particles per cell")
@@ -69,6 +69,11 @@ def workload_config(args, world):
         return {"workload": "inputs/medium.inp as `ipic3d medium.inp` sets it up (Earth dipole, 64x64x64 cells, 10^3 particles per cell = 262144000, "
                             "two-phase initCells), first K steps of the 2400, strong scaling over z-slabs",
                 "particles": 262144000, "particles_per_gpu": 262144000 // world, "grid": [64, 64, 64], "dt": 0.01}
+    if args.workload == "large":
+        return {"workload": "CAPACITY DEMO: inputs/large.inp as `ipic3d large.inp` means it (Earth dipole, 160x160x160 cells, 12^3 particles per cell = "
+                            "7077888000; the reference's int particle count overflows on this deck, so there is no reference run to compare with), "
+                            "universe created on the devices, first K steps, z-slabs",
+                "particles": 7077888000, "particles_per_gpu": 7077888000 // world, "grid": [160, 160, 160], "dt": 0.01}
     return {"workload": "SECONDARY: Earth-dipole .inp set-up of the reference (medium.inp physics, host mirror generator), %dx%dx%d cells, "
                         "8^3 particles per cell, strong scaling over z-slabs" % (g, g, g),
             "particles": g * g * g * 512, "particles_per_gpu": g * g * g * 512 // world, "grid": [g, g, g], "dt": 0.01}
@@ -282,8 +287,8 @@ def parity_gate(args, np, dist, ipic, capi, rank, world, local, flags):
         dist.all_gather_object(out, obj)
         return out
 
-    def slab_ctx(props):
-        ctx = ipic.Context(props, device=local, rank=rank, nranks=world)
+    def slab_ctx(props, zr=None):
+        ctx = ipic.Context(props, device=local, rank=rank, nranks=world, z_begin=zr[0] if zr else None, z_count=zr[1] if zr else None)
         if world > 1:
             ctx.comm_init(bcast(ipic.Context.comm_unique_id() if rank == 0 else None))
         return ctx
@@ -313,16 +318,16 @@ def parity_gate(args, np, dist, ipic, capi, rank, world, local, flags):
         have_ref = bcast(have_ref)
         if not have_ref:
             return {"ran": False, "ok": None, "why": "oracle/_ref not built or not enough host memory for the reference's 16.8 GB universe"}, None
-        props, counts, host = capi.deck_slab_pinned(deck, rank, world, __import__("torch"))
-        nz = int(props.size[2]); nxy = int(props.size[0] * props.size[1]); lz = nz // world
-        with slab_ctx(props) as ctx:
+        props, counts, host, zr = capi.deck_slab_pinned(deck, rank, world, __import__("torch"), balanced=True)
+        nz = int(props.size[2]); nxy = int(props.size[0] * props.size[1]); z0, lz = zr
+        with slab_ctx(props, zr) as ctx:
             ctx.upload_cells_ptr(counts, host.data_ptr())
             del host
             ctx.step(steps, flags)
             got_c, got_p = ctx.download_cells()
         ref_counts = np.load(shm + "_counts.npy")
         ref_p = np.load(shm + "_particles.npy", mmap_mode="r")
-        cells = (np.arange(nxy)[:, None] * nz + rank * lz + np.arange(lz)[None, :]).reshape(-1)
+        cells = (np.arange(nxy)[:, None] * nz + z0 + np.arange(lz)[None, :]).reshape(-1)
         same = bool(np.array_equal(got_c, ref_counts[cells]))
         ep = ev = 0.0
         checked = 0
@@ -335,7 +340,7 @@ def parity_gate(args, np, dist, ipic, capi, rank, world, local, flags):
                 if len(a):
                     ep = max(ep, harness.norm_rel_err(a[:, 0:3], b[:, 0:3])); ev = max(ev, harness.norm_rel_err(a[:, 3:6], b[:, 3:6]))
                     checked += len(a)
-        parts = gather((same, ep, ev, checked, int(got_c.sum())))
+        parts = gather((same, ep, ev, checked, int(got_c.sum()), lz))
         del ref_p
         if world > 1:
             dist.barrier()
@@ -347,7 +352,8 @@ def parity_gate(args, np, dist, ipic, capi, rank, world, local, flags):
                     pass
         ok = all(p[0] for p in parts) and max(p[1] for p in parts) <= 1e-12 and max(p[2] for p in parts) <= 1e-12
         gate["checks"].append({"case": "medium.inp (64^3 cells, 262144000 particles), first %d steps, %d GPU(s)%s vs the reference's own run of the deck" % (
-                                   steps, world, " as NCCL z-slabs" if world > 1 else ""),
+                                   steps, world, " as NCCL z-slabs cut by particle count" if world > 1 else ""),
+                               "planes_per_slab": [p[5] for p in parts],
                                "counts_equal_all_262144_cells": all(p[0] for p in parts), "particles_alive": int(sum(p[4] for p in parts)),
                                "particles_compared": int(sum(p[3] for p in parts)), "max_norm_rel_err_pos": max(p[1] for p in parts),
                                "max_norm_rel_err_vel": max(p[2] for p in parts), "tolerance": 1e-12})
@@ -488,10 +494,13 @@ def run_b200(args):
     if nz % world:
         raise SystemExit("grid z extent %d not divisible by %d ranks" % (nz, world))
     lz = nz // world
+    zr = None                                             # (z_begin, z_count) when the slabs are cut by particle count
     flags = 0 if args.no_deposit else ipic.PROJECT_CURRENT
 
     # ---- parity gate (and, at N = 1, the cpu_baseline leg: the same reference run serves both) ------------------
-    gate, cpu = {"ran": False, "ok": None, "why": "--no-parity-gate"}, None
+    gate, cpu = {"ran": False, "ok": None, "why": "--no-parity-gate" if args.workload != "large" else
+                 "the reference cannot run large.inp (its int particle count overflows, ipic3d.cxx:70-71): no oracle at this size; the same kernels "
+                 "are gated on medium.inp and test.inp"}, None
     if not args.no_parity_gate and args.workload in ("uniform", "medium"):
         gate, cpu = parity_gate(args, np, dist, ipic, capi, rank, world, local, flags)
         if gate.get("ran") and not gate.get("ok"):
@@ -511,19 +520,37 @@ def run_b200(args):
         n_local = int(counts.sum())
         host = torch.from_numpy(np.ascontiguousarray(aos)).pin_memory()
         del aos
+    elif args.workload == "large":
+        # only the device generator can build this universe: 453 GB of particle records would not fit the host
+        args.no_e2e = True
+        free_b, _ = torch.cuda.mem_get_info()
+        if cfg["particles_per_gpu"] * 48 * 2 * 1.3 > free_b:
+            raise SystemExit("large.inp: %.0f GB of particle state per GPU at %d GPUs do not fit (%.0f GB free); use --gpus 8"
+                             % (cfg["particles_per_gpu"] * 48 * 2 * 1.3 / 1e9, world, free_b / 1e9))
+        deck = capi.Deck(os.path.join(ROOT, "tests", "golden", "inputs", "large.inp"))
+        assert deck.num_particles == cfg["particles"]
+        props = capi.Props.from_other(deck.props)
+        planes = capi.balanced_planes(deck.plane_population(), world)
+        zr = (int(sum(planes[:rank])), planes[rank])
+        counts = deck.counts(*zr)
+        n_total = cfg["particles"]
+        n_local = int(counts.sum())
+        host = None
     elif args.workload == "medium" and args.device_init:
         # phase 1 of initCells on the host (sequential by construction, ~2 s), phase 2 on the GPU (ipic_generate_normal_speed)
         args.no_e2e = True
         deck = capi.Deck(os.path.join(ROOT, "tests", "golden", "inputs", "medium.inp"))
         props = capi.Props.from_other(deck.props)
-        counts = deck.counts(rank * lz, lz)
+        planes = capi.balanced_planes(deck.plane_population(), world)
+        zr = (int(sum(planes[:rank])), planes[rank])
+        counts = deck.counts(*zr)
         n_total = cfg["particles"]
         n_local = int(counts.sum())
         host = None
     elif args.workload == "medium":
         # the deck as `ipic3d medium.inp` sets it up; every rank generates ONLY its z-slab (phase 1 of initCells is cheap and
         # replicated, phase 2 is per cell), straight into pinned memory
-        props, counts, host = capi.deck_slab_pinned(os.path.join(ROOT, "tests", "golden", "inputs", "medium.inp"), rank, world, torch)
+        props, counts, host, zr = capi.deck_slab_pinned(os.path.join(ROOT, "tests", "golden", "inputs", "medium.inp"), rank, world, torch, balanced=True)
         n_total = cfg["particles"]
         n_local = int(counts.sum())
     elif args.device_init:
@@ -543,13 +570,13 @@ def run_b200(args):
         capi.uniform_particles_into(props, n_total, host.data_ptr(), rank * lz, lz)
     result = None if args.no_e2e else torch.empty((n_local + n_local // 8 + 4096, 8), dtype=torch.float64).pin_memory()
 
-    ctx = ipic.Context(props, device=local, rank=rank, nranks=world)
+    ctx = ipic.Context(props, device=local, rank=rank, nranks=world, z_begin=zr[0] if zr else None, z_count=zr[1] if zr else None)
     if world > 1:
         uid = [ipic.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0])
     t_init = time.perf_counter()
-    if host is None and args.workload == "medium":
+    if host is None and args.workload in ("medium", "large"):
         ctx.generate_normal_speed(counts, *deck.distribution())
         deck.close()
     elif host is None:
@@ -673,6 +700,7 @@ def run_b200(args):
             "arm": {"what": "B200: fused mover%s + migration through the C ABI (libipic3d_b200.so), z-slab per rank%s" % (
                         "" if args.no_deposit else " + current deposit", ", NCCL send/recv of face messages" if world > 1 else ""),
                     "deposit": not args.no_deposit, "parallelism": "zslab%d" % world, "particle_fields_in_hbm": particle_fields,
+                    "z_planes_of_rank0": list(zr) if zr else [0, lz],
                     "l2": "inputs (%.2f GB of particle state per GPU) are larger than L2; no flush needed" % (n_local * 64 / 1e9),
                     "relayouts_since_upload": relayouts,
                     "universe_into_hbm_s": t_init, "universe_source": "device generator" if host is None else "host generator + upload of pinned AoS"},

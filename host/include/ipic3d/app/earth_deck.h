@@ -25,9 +25,10 @@ namespace ipic3d {
 		InitProperties init;
 		UniverseProperties properties;
 		int numParticles;                                  // an int in the reference as well (it overflows for large.inp)
+		std::int64_t numParticles64;                       // the count the deck means: cells x particles per cell, exact
 
 		explicit EarthDeck(const std::string& path, const std::string& baseName = std::string())
-			: params(path), init(params), properties(params), numParticles(0) {
+			: params(path), init(params), properties(params), numParticles(0), numParticles64(0) {
 			constexpr double earthRadius = 6378137;        // m
 			properties.outputFileBaseName = baseName;
 			properties.dt = 0.01;
@@ -39,9 +40,14 @@ namespace ipic3d {
 			properties.externalMagneticField = { 0.0, 0.0, 3.07e-5 };     // T
 			properties.useCase = UseCase::Dipole;
 			const auto& perCell = init.particlesPerCell[0];
-			numParticles = (int)(properties.size.x * properties.size.y * properties.size.z);
-			numParticles = numParticles * perCell.x * perCell.y * perCell.z;
+			numParticles64 = properties.size.x * properties.size.y * properties.size.z * (std::int64_t)perCell.x * (std::int64_t)perCell.y * (std::int64_t)perCell.z;
+			// `int numParticles = size.x * size.y * size.z; numParticles = numParticles * npcelx * npcely * npcelz;` (ipic3d.cxx:70-71)
+			// wraps around for large.inp (160^3 x 12^3 = 7 077 888 000): reproduced with defined (unsigned) arithmetic
+			numParticles = (int)(std::uint32_t)(std::uint64_t)numParticles64;
 		}
+
+		// does the reference's 32-bit particle count still say what the deck means?  (false for large.inp: the reference cannot run it)
+		bool countFitsReference() const { return numParticles64 == (std::int64_t)numParticles; }
 
 		Vector3<double> boxSize() const { return elementwiseProduct(properties.cellWidth, properties.size); }
 
@@ -60,7 +66,7 @@ namespace ipic3d {
 			return distribution::uniform_pos_normal_speed<>(low, high, Vector3<double>{ 0, 0, 0 }, Vector3<double>{ v, v, v });
 		}
 
-		Universe createUniverse() const { return createUniverseFromDistribution(properties, init, numParticles, protons()); }
+		Universe createUniverse() const { return createUniverseFromDistribution(properties, init, (std::uint64_t)numParticles64, protons()); }
 
 		// the same universe without its particles (grids only): for runs that create the particles on the device
 		// (populateOnDevice in simulator.h) and never need them on the host
@@ -68,7 +74,7 @@ namespace ipic3d {
 
 		// The same universe piecewise, for callers that never hold all of it (one z-slab per GPU / per process):
 		// phase 1 of initCells once (cheap, sequential, identical everywhere), then any cell on its own.
-		std::vector<std::uint64_t> cellPopulations() const { return detail::approximatePopulation(properties, (std::uint64_t)numParticles, protons()); }
+		std::vector<std::uint64_t> cellPopulations() const { return detail::approximatePopulation(properties, (std::uint64_t)numParticles64, protons()); }
 		void populateCell(const coordinate_type& pos, std::uint64_t n, Particle* out) const { detail::populateCell(properties, pos, n, protons(), out); }
 	};
 

@@ -384,10 +384,20 @@ namespace ipic3d {
 					if (cnt[c]) std::memcpy(ps.data(), static_cast<const char*>(staging.p) + offset[c] * sizeof(Particle), (std::size_t)cnt[c] * sizeof(Particle));
 				});
 			}
-			if (fields || current)     // the grids are replicated on every slab: rank 0 has them all
+			if (fields || current)     // E, B, Bc are replicated on every slab: rank 0 has them all (and all of J when a solver ran)
 				check(ipic_download_fields(ctx[0], fields ? reinterpret_cast<double*>(universe.field.data()) : nullptr,
 				                           fields ? reinterpret_cast<double*>(universe.bcfield.data()) : nullptr,
 				                           current ? reinterpret_cast<double*>(universe.currentDensity.data()) : nullptr), "ipic_download_fields");
+			if (current && !fields && gpus > 1) {
+				// projection without a solver: every slab holds J on its own node planes z0 .. z0 + lz only
+				std::vector<DensityNode> part(universe.currentDensity.count());
+				const std::int64_t jy = ny + 1, jz = nz + 1;
+				for (int r = 1; r < gpus; ++r) {
+					check(ipic_download_fields(ctx[(std::size_t)r], nullptr, nullptr, reinterpret_cast<double*>(part.data())), "ipic_download_fields");
+					for (std::int64_t x = 0; x <= props.size.x; ++x) for (std::int64_t y = 0; y <= ny; ++y) for (std::int64_t z = r * lz + 1; z <= (r + 1) * lz; ++z)
+						universe.currentDensity.data()[(x * jy + y) * jz + z] = part[(std::size_t)((x * jy + y) * jz + z)];
+				}
+			}
 		}
 	}
 

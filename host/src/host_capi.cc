@@ -104,7 +104,7 @@ MirrorUniverse* mirrorFromInp(const char* path) {
 	const ipic3d::EarthDeck deck{ std::string(path) };
 	auto* h = new MirrorUniverse(deck.createUniverse());
 	h->ncycles = deck.params.ncycles;
-	h->numParticles = (std::uint64_t)deck.numParticles;
+	h->numParticles = (std::uint64_t)deck.numParticles64;
 	return h;
 }
 
@@ -152,7 +152,7 @@ IPIC_API void* ipic_host_deck_open(const char* path, ipic_props* props, uint64_t
 	std::cout.rdbuf(old);
 	if (props) *props = h->deck.properties.toAbi();
 	if (ncycles) *ncycles = h->deck.params.ncycles;
-	if (numParticles) *numParticles = h->deck.numParticles;
+	if (numParticles) *numParticles = h->deck.numParticles64;
 	return h;
 }
 

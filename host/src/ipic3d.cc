@@ -31,6 +31,13 @@ namespace {
 		// IPIC3D_RESIDENT=0: the reference's flow -- host universe, upload, steps, download of every particle.
 		const char* residentEnv = std::getenv("IPIC3D_RESIDENT");
 		const bool resident = !(residentEnv && std::atoi(residentEnv) == 0);
+		if (!deck.countFitsReference()) {
+			// large.inp: the reference's `int numParticles` overflows (ipic3d.cxx:70-71) and its run is meaningless; here the deck's
+			// exact count is used, which only the device-resident flow can hold (64 B per particle on the host would be 453 GB)
+			std::cout << "Note: " << deck.numParticles64 << " particles exceed the reference's 32-bit count (which reads " << deck.numParticles
+			          << "); using the exact 64-bit count" << std::endl;
+			if (!resident) { std::cerr << "this deck needs the device-resident flow (unset IPIC3D_RESIDENT=0)" << std::endl; return EXIT_FAILURE; }
+		}
 		Universe universe = resident ? deck.createUniverseWithoutParticles() : deck.createUniverse();
 		struct OptionalScope { ResidentScope* s; ~OptionalScope() { delete s; } } scope{ resident ? new ResidentScope(universe) : nullptr };
 		if (resident) {
@@ -43,10 +50,10 @@ namespace {
 
 		std::cout << "Running simulation..." << std::endl;
 		const std::uint64_t cycles = deck.params.ncycles;
-		const int n = deck.numParticles;
+		const double n = (double)deck.numParticles64;
 		const DurationMeasurement t = simulateSteps(cycles, universe);
 
-		std::cout << "Simulation measurements: " << n << " initial particles, first step " << t.firstStep << " seconds, " << (n / t.firstStep)
+		std::cout << "Simulation measurements: " << deck.numParticles64 << " initial particles, first step " << t.firstStep << " seconds, " << (n / t.firstStep)
 		          << " pps, remaining steps " << t.remainingSteps << " seconds, " << (n * (cycles - 1)) / t.remainingSteps << " pps\n"
 		          << "Throughput: " << (cycles * double(n)) / t.remainingSteps << " particles/s \n";
 

@@ -84,6 +84,10 @@ IPIC_API int  ipic_free_pinned(void* p);
  * simulator.h:153-156). `device` is a CUDA ordinal. */
 IPIC_API int  ipic_create(const ipic_props* props, int device, ipic_ctx** out);
 IPIC_API int  ipic_create_slab(const ipic_props* props, int device, int rank, int nranks, ipic_ctx** out);
+/* Slabs need not be equally thick: rank r owns the z-planes [z_begin, z_begin + z_count); the ranks' ranges must tile
+ * [0, nz) in rank order (checked when the slabs first step together).  For universes whose particles are not spread
+ * evenly along z -- the Earth decks fill only the inner 75 % box -- the caller cuts the slabs by particle count. */
+IPIC_API int  ipic_create_slab_range(const ipic_props* props, int device, int rank, int nranks, int z_begin, int z_count, ipic_ctx** out);
 IPIC_API int  ipic_destroy(ipic_ctx* ctx);
 
 /* Head-room of a cell's segment in HBM: room for n*(1+slack) particles, at least n+min_pad.  When an
@@ -118,6 +122,7 @@ IPIC_API int  ipic_set_exchange_capacity(ipic_ctx* ctx, int64_t particles);
  * below (rank r owns the z-planes [r*nz/ndev, (r+1)*nz/ndev)); step all members together with
  * ipic_group_step; destroy each member with ipic_destroy. */
 IPIC_API int  ipic_group_create(const ipic_props* props, const int* devices, int ndev, ipic_ctx** out_ctxs);
+IPIC_API int  ipic_group_create_ranges(const ipic_props* props, const int* devices, int ndev, const int* z_begin, const int* z_count, ipic_ctx** out_ctxs);
 IPIC_API int  ipic_group_step(ipic_ctx** ctxs, int n, uint64_t num_steps, uint32_t flags, double* t_first, double* t_rest);
 
 /* State transfer.  Replaces direct access to universe.cells / .field / .bcfield / .currentDensity
@@ -144,6 +149,11 @@ IPIC_API int  ipic_download_cells(ipic_ctx* ctx, uint64_t* counts, double* parti
 IPIC_API int  ipic_cell_counts(ipic_ctx* ctx, uint64_t* counts);
 IPIC_API int  ipic_total_particles(ipic_ctx* ctx, uint64_t* total);
 IPIC_API int  ipic_upload_fields(ipic_ctx* ctx, const double* field, const double* bcfield, const double* density);
+/* Slab contexts: E, B, Bext, Bc are replicated on every slab (the reference's solvers update in place in a global node
+ * order, so every slab runs them on the whole -- tiny -- grid).  J: with a field solver among the step flags every slab
+ * holds all of it (the slabs all-gather their per-cell corner sums); with the projection alone (IPIC_PROJECT_CURRENT, no
+ * solver) a slab builds J only on its own node planes z_begin .. z_begin + z_count from a one-plane halo of its z-neighbours'
+ * corner sums, and `density` is valid on those planes only. */
 IPIC_API int  ipic_download_fields(ipic_ctx* ctx, double* field, double* bcfield, double* density);
 
 /* The hot path: numSteps iterations of the loop body of simulateSteps (simulator.h:181-230).

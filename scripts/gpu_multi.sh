@@ -10,6 +10,7 @@ uniform) $TR bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/scale_${TAG}_
 uniformq) $TR bench.py --gpus $N --steps 20 --warmup 5 --no-e2e --no-parity-gate > gpurun_out/scaleq_${TAG}_$N.json 2> gpurun_out/scaleq_${TAG}_$N.err; tail -3 gpurun_out/scaleq_${TAG}_$N.err; python scripts/short.py < gpurun_out/scaleq_${TAG}_$N.json ;;
 medium) $TR bench.py --gpus $N --workload medium --steps 20 --warmup 5 --no-e2e > gpurun_out/medium_${TAG}_$N.json 2> gpurun_out/medium_${TAG}_$N.err; tail -3 gpurun_out/medium_${TAG}_$N.err; python scripts/short.py < gpurun_out/medium_${TAG}_$N.json ;;
 mediumq) $TR bench.py --gpus $N --workload medium --steps 20 --warmup 5 --no-e2e --no-parity-gate --device-init > gpurun_out/mediumq_${TAG}_$N.json 2> gpurun_out/mediumq_${TAG}_$N.err; tail -3 gpurun_out/mediumq_${TAG}_$N.err; python scripts/short.py < gpurun_out/mediumq_${TAG}_$N.json ;;
+large) $TR bench.py --gpus $N --workload large --steps 5 --warmup 2 > gpurun_out/large_${TAG}_$N.json 2> gpurun_out/large_${TAG}_$N.err; tail -5 gpurun_out/large_${TAG}_$N.err; python scripts/short.py < gpurun_out/large_${TAG}_$N.json ;;
 ref) python bench.py --impl reference --gpus $N --steps 20 --warmup 5 > gpurun_out/ref_${TAG}_$N.json 2> gpurun_out/ref_${TAG}_$N.err; tail -2 gpurun_out/ref_${TAG}_$N.err; python scripts/short.py < gpurun_out/ref_${TAG}_$N.json ;;
 *) eval "$what" ;;
 esac

@@ -6,7 +6,7 @@ TAG=$1; shift
 Q="--no-e2e --no-cpu-baseline --no-parity-gate"
 for what in "$@"; do
 case $what in
-tests) python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ;;
+tests) python -m pytest tests -m gpu -x -q 2>&1 | tail -40 ;;
 bench) python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; tail -3 gpurun_out/bench_$TAG.err; python scripts/short.py < gpurun_out/bench_$TAG.json ;;
 benchq) python bench.py --steps 20 --warmup 5 $Q > gpurun_out/benchq_$TAG.json 2> gpurun_out/benchq_$TAG.err; tail -3 gpurun_out/benchq_$TAG.err; python scripts/short.py < gpurun_out/benchq_$TAG.json ;;
 refarm) python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/ref_$TAG.json 2> gpurun_out/ref_$TAG.err; tail -3 gpurun_out/ref_$TAG.err; cat gpurun_out/ref_$TAG.json ;;

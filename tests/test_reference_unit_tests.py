@@ -4,7 +4,7 @@ would make.  The binaries are built where /root/reference exists (oracle/Makefil
 oracle/_ref; nothing here reads /root/reference at run time.
 
   init / parameters / particle / universe   pure host code: run in the CPU suite
-  simulation (9 cases)                      simulateSteps / simulateStep on universes the tests build and mutate by hand:
+  simulation (7 cases)                      simulateSteps / simulateStep on universes the tests build and mutate by hand:
                                             Boris straight line, Larmor 1000 steps, ExB drift 5000 steps, migration and
                                             reflection on 3^3 and 4^3 grids -- every step runs on the GPU (-m gpu)
 """
@@ -40,6 +40,8 @@ def test_reference_host_unit_tests_pass_against_the_mirror(name, cases):
 def test_reference_simulation_tests_pass_on_the_gpu():
     """simulation_test.cc: every TEST drives simulateSteps / simulateStep of the mirror, i.e. the CUDA kernels."""
     n, text = run_cases("simulation")
-    assert n >= 8, text[-2000:]
-    for case in ("SingleParticleBorisMover", "SingleParticleLarmorRadius", "SingleParticleBorisMoverExBdrift", "ParticleMigration"):
-        assert re.search(r"OK \] Simulation\.%s" % case, text), case
+    assert n == 7, text[-2000:]
+    for case in ("Simulation.SingleParticleBorisMover", "Simulation.SingleParticleBorisMoverLarmorRadius", "Simulation.SingleParticleLarmorRadius",
+                 "Simulation.SingleParticleBorisMoverExBdrift", "SimulationTest.ParticleMigrationOneDirectionOneParticle",
+                 "SimulationTest.ParticleMigrationTwoDirectionsOneParticle", "SimulationTest.ParticleMigrationManyParticles"):
+        assert "OK ] " + case in text, case
