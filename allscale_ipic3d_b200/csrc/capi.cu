@@ -13,6 +13,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>          // header-only; ranges cost nothing unless a profiler is attached
 
 #include "../../include/ipic3d_b200.h"
 #include "comm.h"
@@ -39,6 +40,12 @@ int fail(int code, const char* fmt, ...) {
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(IPIC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 inline int64_t alignUp(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// NVTX range over a scope: the C ABI entry points and the phases of a slab step show up by name in Nsight timelines
+struct NvtxRange {
+	explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+	~NvtxRange() { nvtxRangePop(); }
+};
 
 } // namespace
 
@@ -341,6 +348,15 @@ int relayoutAfterOverflow(ipic_ctx* c, int outGen, int failedStep) {
 	struct Fresh { ParticleArrays* nb; unsigned char** tag; unsigned short** order; int64_t** start; bool armed;
 	               ~Fresh() { if (armed) { cudaFree(nb[0].d); cudaFree(nb[1].d); cudaFree(*tag); cudaFree(*order); cudaFree(*start); } } } fresh{ nb, &ntag, &norder, &dNewStart, true };
 	const int64_t nslots = newStart.back();
+	{
+		// the new storage lives beside the old one until the heads and the failed import have been redone
+		size_t freeB = 0, totalB = 0;
+		const double needB = (double)nslots * (2.0 * c->g.nf * sizeof(double) + 1 + sizeof(unsigned short));
+		if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess && needB > (double)freeB)
+			return fail(IPIC_ERR_CAPACITY, "rank %d: a cell segment overflowed in step %d and the re-layout needs %.1f GB beside the live storage, %.1f GB are free: "
+			                               "use more GPUs (thinner slabs) or give the cells more head-room up front (ipic_set_headroom)",
+			            c->rank, failedStep, needB / 1e9, (double)freeB / 1e9);
+	}
 	rc = allocParticleBuffers(nb, &ntag, &norder, nslots, c->g.nf);
 	if (rc) return rc;
 	CK(cudaMalloc(&dNewStart, newStart.size() * sizeof(int64_t)));
@@ -619,6 +635,7 @@ int establishLayout(ipic_ctx* c, const std::vector<int64_t>& need, int nf, doubl
 } // namespace
 
 int ipic_upload_cells(ipic_ctx* c, const uint64_t* counts, const double* aos) {
+	NvtxRange nvtx("ipic_upload_cells");
 	if (!c || !counts) return fail(IPIC_ERR_ARG, "null argument");
 	CK(cudaSetDevice(c->device));
 	{ int rcA = settleAsync(c); if (rcA) return rcA; }
@@ -751,6 +768,7 @@ int ipic_total_particles(ipic_ctx* c, uint64_t* total) {
 }
 
 int ipic_download_cells(ipic_ctx* c, uint64_t* counts, double* aos, uint64_t capacity) {
+	NvtxRange nvtx("ipic_download_cells");
 	if (!c || !counts) return fail(IPIC_ERR_ARG, "null argument");
 	CK(cudaSetDevice(c->device));
 	{ int rcA = settleAsync(c); if (rcA) return rcA; }
@@ -903,6 +921,7 @@ void spanEnd(ipic_ctx* c, cudaEvent_t* pendingEnd) {
 
 // the whole universe on one GPU: no exchange
 int enqueueStepSingle(ipic_ctx* c, const StepFlags& f, int stepIndex) {
+	NvtxRange nvtx("step:enqueue");
 	if (f.project && f.interp) {
 		depositPass(c, f, 0, c->g.lz);
 		launch_gather_current(c->g, c->dCellJ, c->dJ, c->dStop, c->stream);
@@ -1155,6 +1174,9 @@ FacePieces piecesOf(const ipic_ctx* c, char* base, int cap, int total) {
 }
 
 int slabPhase(ipic_ctx* c, int phase, const StepFlags& f, int stepIndex) {
+	static const char* const kPhaseName[] = { "slab:pre_deposit", "slab:pre_gather_J", "slab:boundary_movers+pack", "slab:interior_mover", "slab:settle",
+	                                          "slab:exchange", "slab:gather_J", "slab:import", "slab:fields" };
+	NvtxRange nvtx(kPhaseName[phase]);
 	CK(cudaSetDevice(c->device));
 	const int lz = c->g.lz;
 	switch (phase) {
@@ -1531,6 +1553,7 @@ int ipic_sync(ipic_ctx* c) {
 }
 
 int ipic_step(ipic_ctx* c, uint64_t numSteps, uint32_t flags, double* tFirst, double* tRest) {
+	NvtxRange nvtx("ipic_step");
 	if (tFirst) *tFirst = 0;
 	if (tRest) *tRest = 0;
 	{ int rc = checkSoloStep(c, flags); if (rc) return rc; }
@@ -1593,6 +1616,7 @@ int ipic_group_create_ranges(const ipic_props* props, const int* devices, int nd
 }
 
 int ipic_group_step(ipic_ctx** ctxs, int n, uint64_t numSteps, uint32_t flags, double* tFirst, double* tRest) {
+	NvtxRange nvtx("ipic_group_step");
 	if (tFirst) *tFirst = 0;
 	if (tRest) *tRest = 0;
 	if (!ctxs || n < 1 || !ctxs[0]) return fail(IPIC_ERR_ARG, "bad group arguments");

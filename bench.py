@@ -175,7 +175,7 @@ def reference_universe(args, n_particles):
     return r, (r.threads() if threaded else 1)
 
 
-def time_reference(args, n_particles, steps, warmup, deposit=False, keep=False):
+def time_reference(args, n_particles, steps, warmup, deposit=False, keep=False, world=None):
     """`warmup` + `steps` steps of the reference's own time loop on all host threads; returns (result dict, universe or None)."""
     harness = _harness()
     r, cores = reference_universe(args, n_particles)
@@ -187,7 +187,7 @@ def time_reference(args, n_particles, steps, warmup, deposit=False, keep=False):
     t = r.step(steps, flags)
     res = {"value": steps * n_particles / t, "seconds": t, "cores": cores, "kind": "reference", "unit": UNIT,
            "sample": "%d particles (%s), %d warm-up + %d timed steps of %s, %d host threads" % (
-               n_particles, "the whole workload" if n_particles == workload_config(args, int(os.environ.get("WORLD_SIZE", "1")))["particles"] else "bounded sample of the workload",
+               n_particles, "the whole workload" if n_particles == workload_config(args, world or int(os.environ.get("WORLD_SIZE", "1")))["particles"] else "bounded sample of the workload",
                warmup, steps,
                "ref_step_full (projectToDensityField + mover + export/import, the order of the commented loop simulator.h:189-223)" if deposit
                else "simulateSteps as shipped (mover + export/import; STEP 1 is commented out in the reference, simulator.h:189-200)", cores)}
@@ -212,13 +212,13 @@ def run_reference(args):
             n //= 2
         bounded = "host memory: sample of %d particles instead of %d" % (n, cfg["particles"])
     t0 = time.time()
-    res, _ = time_reference(args, n, args.steps, args.warmup, deposit=False)
+    res, _ = time_reference(args, n, args.steps, args.warmup, deposit=False, world=world)
     if res is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (reference sources absent at build time)"}))
         return 0
     # second, labelled number: the same loop WITH the reference's own projectToDensityField (what our arm fuses in)
     dep_steps = max(1, min(args.steps, 5))
-    dep, _ = time_reference(args, n, dep_steps, 1, deposit=True) if args.workload == "uniform" else (None, None)
+    dep, _ = time_reference(args, n, dep_steps, 1, deposit=True, world=world) if args.workload == "uniform" else (None, None)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds"] / args.steps * 1e3, "higher_is_better": True,
@@ -718,7 +718,15 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    return run_b200(args)
+    try:
+        return run_b200(args)
+    except BaseException as e:      # noqa: BLE001 -- a failing rank must take the job down at once: its peers would wait in NCCL for ever
+        if isinstance(e, SystemExit) and not e.code:
+            return 0
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(1)
 
 
 if __name__ == "__main__":
