@@ -1498,7 +1498,7 @@ static int finishSingleBatch(ipic_ctx* c, int genAtStart, uint64_t numSteps, uin
 		int stop[8];
 		CK(cudaMemcpy(stop, c->dStop, sizeof stop, cudaMemcpyDeviceToHost));
 		c->sortLikely = stop[5] != 0;
-		if (stop[5]) CK(cudaMemset(c->dStop + 5, 0, sizeof(int)));
+		if (stop[5]) CK(cudaMemsetAsync(c->dStop + 5, 0, sizeof(int), c->stream));      // ordered before the next batch's movers
 		if (!stop[0]) return IPIC_OK;
 		// import of step `stop[1]` of this batch overflowed; later steps were skipped on the device
 		const int failed = stop[1];

@@ -54,8 +54,19 @@ namespace ipic3d {
 		struct default_particle_mover {};
 		struct interpolating_particle_mover {};
 
+		template<typename T, typename... Known> struct is_one_of : std::false_type {};
+		template<typename T, typename K, typename... Rest> struct is_one_of<T, K, Rest...> : std::conditional<std::is_same<T, K>::value, std::true_type, is_one_of<T, Rest...>>::type {};
+
 		template<typename Projector, typename Solver, typename Mover>
 		constexpr std::uint32_t stepFlags() {
+			// the policy parameters are TAGS for device kernels: a user-written functor cannot cross to the GPU, and silently
+			// running the default in its place would be worse than not compiling
+			static_assert(is_one_of<Projector, default_particle_to_field_projector, current_density_projector>::value,
+			              "ParticleToFieldProjector must be one of the tags in ipic3d::detail (functors do not run on the device)");
+			static_assert(is_one_of<Solver, default_field_solver, forward_field_solver, leapfrog_field_solver>::value,
+			              "FieldSolver must be one of the tags in ipic3d::detail (functors do not run on the device)");
+			static_assert(is_one_of<Mover, default_particle_mover, interpolating_particle_mover>::value,
+			              "ParticleMover must be one of the tags in ipic3d::detail (functors do not run on the device)");
 			std::uint32_t f = 0;
 			if (std::is_same<Solver, forward_field_solver>::value) f |= IPIC_PROJECT_CURRENT | IPIC_UPDATE_BOUNDARIES | IPIC_SOLVER_FORWARD;
 			if (std::is_same<Solver, leapfrog_field_solver>::value) f |= IPIC_PROJECT_CURRENT | IPIC_UPDATE_BOUNDARIES | IPIC_SOLVER_LEAPFROG;

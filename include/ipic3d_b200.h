@@ -61,7 +61,9 @@ typedef struct {
 enum {
 	IPIC_MOVER_DIPOLE_ANALYTIC = 0u,      /* detail::default_particle_mover as shipped: E=0, analytic dipole B (cell.h:896-964) */
 	IPIC_MOVER_INTERPOLATED    = 1u << 0, /* the commented-out corner gather + trilinearInterpolationF2P (cell.h:905-937, :867-885) */
-	IPIC_PROJECT_CURRENT       = 1u << 1, /* detail::default_particle_to_field_projector → projectToDensityField (cell.h:787-824) */
+	IPIC_PROJECT_CURRENT       = 1u << 1, /* detail::default_particle_to_field_projector → projectToDensityField (cell.h:787-824);
+	                                         the per-cell sums are formed in another (fixed, reproducible) order than the reference's
+	                                         sequential loop: J agrees within 1e-12 of max|J|, not bit for bit */
 	IPIC_SOLVER_FORWARD        = 1u << 2, /* detail::forward_field_solver  → solveFieldForward  (field.h:294-337) */
 	IPIC_SOLVER_LEAPFROG       = 1u << 3, /* detail::leapfrog_field_solver → solveFieldLeapfrog (field.h:342-402) */
 	IPIC_UPDATE_BOUNDARIES     = 1u << 4, /* updateFieldsOnBoundaries before the solve (field.h:407-440, simulator.h:204) */

@@ -37,6 +37,20 @@ def test_test_inp_out_file_matches_reference(tmp_path, devices):
     assert re.search(r"Throughput: [0-9.e+]+ particles/s", text)
 
 
+def test_resident_and_host_universe_flows_agree(tmp_path):
+    """`ipic3d test.inp` creates, steps and counts its universe in HBM by default (device generator, resident mode, `.out` from
+    the device's per-cell counters); IPIC3D_RESIDENT=0 is the reference's flow (host universe, upload, steps, download of all
+    particles, host writer).  Same `.out`, byte for byte."""
+    a, b = tmp_path / "resident", tmp_path / "host"
+    a.mkdir(); b.mkdir()
+    run(DRIVER, DECK, str(a))
+    run(DRIVER, DECK, str(b), {"IPIC3D_RESIDENT": "0"})
+    assert (a / "test.out").read_text() == (b / "test.out").read_text()
+    t1 = run(DRIVER, ":U:1000000", str(a))
+    t2 = run(DRIVER, ":U:1000000", str(b), {"IPIC3D_RESIDENT": "0"})
+    assert "Throughput:" in t1 and "Throughput:" in t2
+
+
 def test_missing_file_and_usage(tmp_path):
     """Error behaviour of the reference's main (ipic3d.cxx:18-21) and parser (parameters.h:148-151)."""
     r = subprocess.run([DRIVER], capture_output=True, text=True)

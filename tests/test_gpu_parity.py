@@ -35,8 +35,8 @@ def load_props(raw):
 def assert_particles_close(got, want, tol=TOL):
     assert got.shape == want.shape
     assert bits_equal(got[:, 6:8], want[:, 6:8])                 # q, qom are carried, never recomputed
-    assert norm_rel_err(got[:, 0:3], want[:, 0:3]) <= tol
-    assert norm_rel_err(got[:, 3:6], want[:, 3:6]) <= tol
+    ep, ev = norm_rel_err(got[:, 0:3], want[:, 0:3]), norm_rel_err(got[:, 3:6], want[:, 3:6])
+    assert ep <= tol and ev <= tol, "norm-relative error: positions %.3g, velocities %.3g (tolerance %.1g)" % (ep, ev, tol)
 
 
 def test_division_selftest():
@@ -61,7 +61,9 @@ def test_small_dipole_golden(golden_dir):
         c.step(19)
         counts, aos = c.download_cells()
         assert np.array_equal(counts, g["counts20"])
-        assert_particles_close(aos, g["p20"], tol=1e-11)   # free-running 20 steps of chaotic gyration
+        # free-running 20 steps of chaotic gyration: the reference itself, built with and without FMA contraction, drifts apart by
+        # 3.3e-13 on this fixture (measured in the build container); the bar stays north_star's 1e-12
+        assert_particles_close(aos, g["p20"])
         assert c.count_misplaced() == harness_misplaced(props, g["counts20"], g["p20"])
 
 
@@ -194,7 +196,7 @@ def test_full_pic_step_golden(golden_dir, solver):
     # J enters E with different rounding in the last bits, so E/B/particles are compared to 1e-12 as well
     for got, want in ((f, g[solver + "_field"]), (b, g[solver + "_bc"])):
         assert np.max(np.abs(got - want)) <= TOL * np.max(np.abs(want))
-    assert_particles_close(aos, g[solver + "_p"], tol=1e-11)
+    assert_particles_close(aos, g[solver + "_p"])
 
 
 def test_interpolating_mover_bit_exact(golden_dir):
