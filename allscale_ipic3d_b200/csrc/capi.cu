@@ -87,6 +87,7 @@ struct ipic_ctx {
 	int64_t meanPopulation = 0;                    // particles per owned cell at upload (drives the mover's tile shape)
 	double slack = 0.25;                           // head-room per cell as a fraction of its population
 	int64_t minPad = 64;                           // ... and in absolute slots
+	double neighbourShare = 0.0;                   // adaptive head-room per cell: this share of the fullest of its 26 neighbours (0 = off)
 	int64_t padFloor = 0;                          // adaptive absolute head-room: a share of the MEAN population, for universes whose sparse
 	                                               // cells fill up (dipole runs start with 12 particles in the outer cells); doubles per re-layout
 	bool userHeadroom = false;                     // ipic_set_headroom was called: no automatic floor at upload
@@ -167,17 +168,35 @@ int allocParticleBuffers(ParticleArrays out[2], unsigned char** tag, unsigned sh
 	return IPIC_OK;
 }
 
-// capacity of a cell segment that currently needs room for n particles
-int64_t capacityFor(const ipic_ctx* c, int64_t n) {
-	return alignUp(n + std::max<int64_t>(std::max<int64_t>((int64_t)std::ceil((double)n * c->slack), c->minPad), c->padFloor), kSlotAlign);
+// capacity of a cell segment that currently needs room for n particles (localFloor: what its surroundings suggest, below)
+int64_t capacityFor(const ipic_ctx* c, int64_t n, int64_t localFloor = 0) {
+	const int64_t pad = std::max<int64_t>(std::max<int64_t>((int64_t)std::ceil((double)n * c->slack), c->minPad), std::max(c->padFloor, localFloor));
+	return alignUp(n + pad, kSlotAlign);
 }
 
-// segment layout of the slab's cells: capacity for the current population plus head-room
+// segment layout of the slab's cells: capacity for the current population plus head-room.  With neighbourShare > 0 (set for
+// universes that hold sparse cells next to full ones) a cell also gets room for that share of its fullest neighbour's
+// population: particles diffuse from full cells into the empty ones beside them (the shell around the Earth decks' inner
+// box; the cell ahead of a beam), and how much can arrive is a matter of the neighbours, not of the slab's mean.
 void buildLayout(const ipic_ctx* c, const std::vector<int64_t>& need, std::vector<int64_t>& start) {
 	const Geometry& g = c->g;
 	start.assign((size_t)g.ncellsLocal + 1, 0);
 	int64_t pos = 0;
-	for (int cell = 0; cell < g.ncellsLocal; cell++) { start[(size_t)cell] = pos; pos += capacityFor(c, need[(size_t)cell]); }
+	for (int cell = 0; cell < g.ncellsLocal; cell++) {
+		int64_t localFloor = 0;
+		if (c->neighbourShare > 0.0) {
+			const int xy = cell / g.lz, zl = cell - xy * g.lz, cx = xy / g.ny, cy = xy - cx * g.ny;
+			int64_t fullest = 0;
+			for (int a = -1; a <= 1; a++) for (int b = -1; b <= 1; b++) for (int d = -1; d <= 1; d++) {
+				const int x = (cx + a + g.nx) % g.nx, y = (cy + b + g.ny) % g.ny;
+				const int z = std::min(std::max(zl + d, 0), g.lz - 1);              // beyond the slab: the boundary plane stands in
+				fullest = std::max(fullest, need[(size_t)((x * g.ny + y) * g.lz + z)]);
+			}
+			localFloor = (int64_t)(c->neighbourShare * (double)fullest);
+		}
+		start[(size_t)cell] = pos;
+		pos += capacityFor(c, need[(size_t)cell], localFloor);
+	}
 	start[(size_t)g.ncellsLocal] = pos;
 }
 
@@ -548,7 +567,7 @@ int ipic_destroy(ipic_ctx* c) {
 int ipic_set_headroom(ipic_ctx* c, double slack, int64_t minPad) {
 	if (!c || !(slack >= 0) || minPad < 0) return fail(IPIC_ERR_ARG, "bad head-room");
 	c->slack = slack; c->minPad = minPad;
-	c->userHeadroom = true; c->padFloor = 0;
+	c->userHeadroom = true; c->padFloor = 0; c->neighbourShare = 0.0;
 	return IPIC_OK;
 }
 
@@ -588,6 +607,9 @@ int establishLayout(ipic_ctx* c, const std::vector<int64_t>& need, int nf, doubl
 		const int64_t mean = total / std::max(1, nOwned);
 		const int64_t least = need.empty() ? 0 : *std::min_element(need.begin(), need.end());
 		c->padFloor = least < mean / 4 ? mean + mean / 4 : 0;
+		// ... and for what its fullest neighbour can send it: the slab's mean says little when most of the slab is empty (medium.inp
+		// on 8 GPUs: the outer slabs hold 8 empty planes beside 6 full ones, a floor of 1.25 x their mean overflowed within ten steps)
+		c->neighbourShare = least < mean / 4 ? 0.6 : 0.0;
 	}
 	std::vector<int64_t> start;
 	buildLayout(c, need, start);
@@ -599,8 +621,9 @@ int establishLayout(ipic_ctx* c, const std::vector<int64_t>& need, int nf, doubl
 		if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
 			const double perSlot = 2.0 * nf * sizeof(double) + 1 + sizeof(unsigned short);
 			const double have = 0.85 * ((double)freeB + (double)c->slots * (2.0 * c->slotsNf * sizeof(double) + 3));
-			while (c->padFloor > 64 && (double)start.back() * perSlot > have) {
+			while ((c->padFloor > 64 || c->neighbourShare > 0.01) && (double)start.back() * perSlot > have) {
 				c->padFloor /= 2;
+				c->neighbourShare /= 2;
 				buildLayout(c, need, start);
 			}
 		}
