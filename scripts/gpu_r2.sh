@@ -39,6 +39,11 @@ dipvar)
     echo -n "dipole [$v] : "; env $v python bench.py --workload dipole --steps 20 --warmup 12 $Q 2>/dev/null | python scripts/short.py | cut -d'|' -f1-4
   done ;;
 medium) python bench.py --workload medium --steps 20 --warmup 5 > gpurun_out/medium_$TAG.json 2> gpurun_out/medium_$TAG.err; tail -3 gpurun_out/medium_$TAG.err; python scripts/short.py < gpurun_out/medium_$TAG.json ;;
+ncurest)
+  for k in k_solver_wavefront k_init_deck_positions k_init_normal_speed k_copy_heads; do
+    timeout 60 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o /tmp/prof_${k} python scripts/probe_kernels.py > /tmp/ncu_${k}.log 2>&1
+    python scripts/ncu_summary.py /tmp/prof_${k}.ncu-rep --mix --top 8 > gpurun_out/${TAG}_${k}_summary.txt 2>&1; rm -f /tmp/prof_${k}.ncu-rep
+  done ;;
 sanitize)
   timeout 240 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/sanitize_case.py > gpurun_out/memcheck_$TAG.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/memcheck_$TAG.log
   timeout 150 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/sanitize_case.py > gpurun_out/racecheck_$TAG.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/racecheck_$TAG.log

@@ -47,6 +47,12 @@ with ipic.Group(props, [0, 0]) as g:                        # two slabs on one G
     g.upload_cells(counts, aos)
     g.step(3, ipic.PROJECT_CURRENT)
 
+deck = os.path.join(ROOT, "tests", "golden", "inputs", "tiny.inp")
+with capi.Deck(deck) as d, ipic.Context(d.props) as c:      # k_init_deck_positions, k_init_normal_speed (2 M particles), dipole k_move, k_sort_outbox
+    d.generate_on_device(c)
+    c.step(2, ipic.PROJECT_CURRENT)
+    print("deck", c.total_particles())
+
 tp = capi.Props.make(16, cellWidth=(7.97267e6 / 2,) * 3, dt=0.01, speedOfLight=299792458.0, planetRadius=6378137.0,
                      origin=(-8 * 7.97267e6 / 2,) * 3, externalMagneticField=(0.0, 0.0, 3.07e-5))
 rng = np.random.default_rng(1)
