@@ -11,7 +11,9 @@
 // plane in parallel reproduces the sequential result bit for bit.
 #include "field_kernels.h"
 
+#include <cooperative_groups.h>
 #include <cstdlib>
+#include <cstring>
 
 namespace ipic {
 
@@ -125,11 +127,14 @@ __global__ void k_solver_node(const Geometry g, double* EB, double* Bc, const do
 	if (FORWARD) solve_forward_node(g, EB, Bc, J, x, y, z); else solve_leapfrog_node(g, EB, Bc, J, x, y, z);
 }
 
-// The whole sweep in ONE launch: a single CTA of 512 threads (the forward solver's node update wants ~100 registers) walks
-// the hyperplanes in order with a block barrier between them.  A plane holds at most ~3/4 (n+1)^2 nodes (817 at 32^3),
-// i.e. one or two nodes per thread; what the
-// sweep costs is the dependency chain plane -> plane, and a __syncthreads (which also makes the plane's stores
-// visible to the block) is far cheaper than a kernel boundary: ~1 us instead of ~3 us per plane, 99 planes at 32^3.
+// ---- the sweep over the hyperplanes ----------------------------------------------------------------------------------
+// What the sweep costs is its dependency chain: 99 planes at 32^3, each a few hundred nodes of ~80 scattered 8-byte loads.
+// Measured on B200 (scripts/probe_solver.py, forward solver, per step): one launch per plane 0.72 ms (a kernel boundary per
+// plane); ONE CTA walking all planes with __syncthreads 1.11 ms (a single SM's load/store unit serialises the plane: ncu
+// lg_throttle 4.6, long scoreboard 8.4 per issue); a cooperative launch of as many CTAs as the per-plane grid had, with a
+// grid-wide barrier per plane: see DESIGN.md 3.  IPIC_SOLVER_MODE = coop | planes | one selects; a cooperative launch that
+// the device refuses falls back to one launch per plane.
+
 template<bool FORWARD>
 __global__ void __launch_bounds__(512)
 k_solver_wavefront(const Geometry g, double* EB, double* Bc, const double* J, const int* stopFlag) {
@@ -146,19 +151,52 @@ k_solver_wavefront(const Geometry g, double* EB, double* Bc, const double* J, co
 	}
 }
 
-static bool solver_one_launch() {
+// all CTAs of a cooperative launch walk the planes together: grid.sync() orders the plane's stores before the next plane's loads
+template<bool FORWARD>
+__global__ void __launch_bounds__(128)
+k_solver_coop(const Geometry g, double* EB, double* Bc, const double* J, const int* stopFlag) {
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	if (*stopFlag) return;                               // the same word for every thread of the grid: nobody reaches a barrier
+	const int ex = g.nx + 1, ey = g.ny + 1;
+	const int lo = 3, hi = ex + ey + (g.nz + 1);
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool mine = t < ex * ey;
+	const int x = 1 + t / ey, y = 1 + t % ey;
+	for (int plane = lo; plane <= hi; plane++) {
+		const int z = plane - x - y;
+		if (mine && z >= 1 && z <= g.nz + 1) {
+			if (FORWARD) solve_forward_node(g, EB, Bc, J, x, y, z); else solve_leapfrog_node(g, EB, Bc, J, x, y, z);
+		}
+		grid.sync();
+	}
+}
+
+static int solver_mode() {          // 0 planes, 1 one CTA, 2 cooperative
 	static int v = -1;
-	if (v < 0) { const char* e = std::getenv("IPIC_SOLVER_LAUNCHES"); v = (e && std::atoi(e) != 0) ? 0 : 1; }   // IPIC_SOLVER_LAUNCHES=1: one launch per hyperplane
-	return v != 0;
+	if (v < 0) {
+		const char* e = std::getenv("IPIC_SOLVER_MODE");
+		v = 2;
+		if (e && std::strcmp(e, "planes") == 0) v = 0;
+		if (e && std::strcmp(e, "one") == 0) v = 1;
+	}
+	return v;
 }
 
 int launch_field_solver(const Geometry& g, bool forward, double* EB, double* Bc, const double* J, const int* stopFlag, cudaStream_t st) {
 	const int threads = (g.nx + 1) * (g.ny + 1);
 	const int lo = 3, hi = (g.nx + 1) + (g.ny + 1) + (g.nz + 1);
-	if (solver_one_launch()) {
+	const int mode = solver_mode();
+	if (mode == 1) {
 		if (forward) k_solver_wavefront<true><<<1, 512, 0, st>>>(g, EB, Bc, J, stopFlag);
 		else k_solver_wavefront<false><<<1, 512, 0, st>>>(g, EB, Bc, J, stopFlag);
 		return 1;
+	}
+	if (mode == 2) {
+		Geometry gg = g;
+		void* args[] = { &gg, &EB, &Bc, &J, &stopFlag };
+		const void* kernel = forward ? (const void*)k_solver_coop<true> : (const void*)k_solver_coop<false>;
+		if (cudaLaunchCooperativeKernel(kernel, dim3((threads + 127) / 128), dim3(128), args, 0, st) == cudaSuccess) return 1;
+		cudaGetLastError();                              // refused (grid too large to be co-resident, or no support): per-plane launches
 	}
 	int launches = 0;
 	for (int p = lo; p <= hi; p++) {
