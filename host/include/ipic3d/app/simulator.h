@@ -244,6 +244,7 @@ namespace ipic3d {
 	>
 	DurationMeasurement simulateSteps(std::uint64_t numSteps, Universe& universe) {
 		using clock = std::chrono::high_resolution_clock;
+		// (the reference truncates to milliseconds, hdr/simulator.h:122; whole runs take a few of them here, so microseconds)
 		const auto seconds = [](clock::duration d) { return std::chrono::duration_cast<std::chrono::microseconds>(d).count() / 1e6; };
 		const std::uint32_t flags = detail::stepFlags<ParticleToFieldProjector, FieldSolver, ParticleMover>();
 		const bool usesFields = flags & (IPIC_MOVER_INTERPOLATED | IPIC_SOLVER_FORWARD | IPIC_SOLVER_LEAPFROG | IPIC_UPDATE_BOUNDARIES);
