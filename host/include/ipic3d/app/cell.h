@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "ipic3d/app/field.h"
 #include "ipic3d/app/init_properties.h"
 #include "ipic3d/app/parameters.h"
 #include "ipic3d/app/particle.h"
@@ -334,6 +335,43 @@ namespace ipic3d {
 			}
 		});
 		return cells;
+	}
+
+	// ---- scalar versions of two per-timestep pieces, host-callable for known-answer checks ----------------------------
+	// ("host-callable scalar versions ... stay available for the KATs").  `simulateSteps` never calls them:
+	// in the time loop the interpolation is `trilinear` of the interpolating mover and the projection is the per-cell corner
+	// sums of the movers plus k_gather_current (csrc/particle_kernels.cu).  The movers, export and import have no host
+	// version at all.
+
+	// value at the fractional position `pos` in [0,1]^3 between 8 corner values, divided by `vol` (reference hdr/cell.h:867-885)
+	template<typename T>
+	T trilinearInterpolationF2P(const T corners[2][2][2], const Vector3<double>& pos, const double vol) {
+		const double along[3][2] = { { 1 - pos.x, pos.x }, { 1 - pos.y, pos.y }, { 1 - pos.z, pos.z } };
+		T res = T(0);
+		for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) for (int k = 0; k < 2; ++k)
+			res += corners[i][j][k] * (along[0][i] * along[1][j] * along[2][k]);
+		return res / vol;
+	}
+
+	// J on node `pos` = sum over the particles of the 8 cells around the node (periodic) of q v w, w the trilinear weight of
+	// the node seen from the particle's cell, divided by the cell volume and by 8 (reference hdr/cell.h:787-824)
+	inline void projectToDensityField(const UniverseProperties& universeProperties, const Cells& cells, const coordinate_type& pos, CurrentDensity& density) {
+		const coordinate_type size = universeProperties.size;
+		Vector3<double> Js(0.0);
+		// a = 0: the cell below the node along that axis (the node is its upper corner: weight = relative position),
+		// a = 1: the cell above (the node is its lower corner: weight = 1 - relative position)
+		for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) {
+			coordinate_type cur{ pos.x + a - 1, pos.y + b - 1, pos.z + c - 1 };
+			for (int d = 0; d < 3; ++d) cur[d] = cur[d] < 0 ? size[d] - 1 : (cur[d] >= size[d] ? 0 : cur[d]);
+			const Vector3<double> cellOrigin = getOriginOfCell(cur, universeProperties);
+			for (const Particle& p : cells[cur].particles) {
+				const Vector3<double> rel = elementwiseDivision(p.position - cellOrigin, universeProperties.cellWidth);
+				const double fac = (a ? 1 - rel.x : rel.x) * (b ? 1 - rel.y : rel.y) * (c ? 1 - rel.z : rel.z);
+				Js += p.q * p.velocity * fac;
+			}
+		}
+		const double vol = universeProperties.cellWidth.x * universeProperties.cellWidth.y * universeProperties.cellWidth.z;
+		density[pos].J = (Js / vol) / 8.0;
 	}
 
 	// ---- conserved-quantity folds over a host universe (reference hdr/cell.h:1315-1355) --------------------------

@@ -232,6 +232,38 @@ IPIC_API void ipic_mirror_get_fields(void* handle, double* field, double* bc, do
 	std::memcpy(J, u.currentDensity.data(), u.currentDensity.count() * sizeof(ipic3d::DensityNode));
 }
 
+IPIC_API void ipic_mirror_set_fields(void* handle, const double* field, const double* bc, const double* J) {
+	auto& u = static_cast<MirrorUniverse*>(handle)->universe;
+	if (field) std::memcpy(u.field.data(), field, u.field.count() * sizeof(ipic3d::FieldNode));
+	if (bc) std::memcpy(u.bcfield.data(), bc, u.bcfield.count() * sizeof(ipic3d::BcFieldCell));
+	if (J) std::memcpy(u.currentDensity.data(), J, u.currentDensity.count() * sizeof(ipic3d::DensityNode));
+}
+
+// the host-callable scalar versions of the per-node pieces (cell.h / field.h mirror; never used by simulateSteps), on one
+// node: op 0 = projectToDensityField, 1 = solveFieldForward, 2 = solveFieldLeapfrog; op 3 = updateFieldsOnBoundaries
+IPIC_API int ipic_mirror_node_op(void* handle, int op, int64_t x, int64_t y, int64_t z) {
+	using namespace ipic3d;
+	auto& u = static_cast<MirrorUniverse*>(handle)->universe;
+	const coordinate_type pos{ x, y, z };
+	switch (op) {
+	case 0: projectToDensityField(u.properties, u.cells, pos, u.currentDensity); return IPIC_OK;
+	case 1: solveFieldForward(u.properties, pos, u.currentDensity, u.field, u.bcfield); return IPIC_OK;
+	case 2: solveFieldLeapfrog(u.properties, pos, u.currentDensity, u.field, u.bcfield); return IPIC_OK;
+	case 3: updateFieldsOnBoundaries(u.field, u.bcfield); return IPIC_OK;
+	}
+	return IPIC_ERR_ARG;
+}
+
+// value of trilinearInterpolationF2P for 8 corner vectors [i][j][k][component] at a fractional position
+IPIC_API void ipic_mirror_trilinear(const double* corners24, const double* pos3, double vol, double* out3) {
+	using namespace ipic3d;
+	Vector3<double> corners[2][2][2];
+	for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) for (int k = 0; k < 2; ++k)
+		corners[i][j][k] = { corners24[((i * 2 + j) * 2 + k) * 3], corners24[((i * 2 + j) * 2 + k) * 3 + 1], corners24[((i * 2 + j) * 2 + k) * 3 + 2] };
+	const Vector3<double> r = trilinearInterpolationF2P(corners, Vector3<double>{ pos3[0], pos3[1], pos3[2] }, vol);
+	out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+
 // the particles pic_tracer's generator produces for one task (pic_tracer.cxx:236-262): seed = a*b of the task
 IPIC_API void ipic_mirror_tracer_particles(const ipic_props* props, uint32_t seed, uint64_t n, double* aos) {
 	using namespace ipic3d;

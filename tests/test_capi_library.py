@@ -74,3 +74,23 @@ def test_host_tree_never_touches_the_oracle():
                     text = open(os.path.join(dirpath, f), errors="ignore").read()
                     assert "oracle" not in text.lower(), \
                         "%s refers to the oracle tree" % os.path.join(dirpath, f)
+
+
+def test_time_loop_never_calls_the_host_scalar_versions():
+    """The mirror keeps host-callable scalar versions of a few per-node functions for known-answer checks (cell.h:
+    projectToDensityField, trilinearInterpolationF2P; field.h: curls, solvers, ghost update).  The time loop and the drivers
+    must not use them -- simulateSteps steps on the GPU or fails -- and movers / export / import have no host version."""
+    import re
+    scalar = r"\b(projectToDensityField|trilinearInterpolationF2P|solveFieldForward|solveFieldLeapfrog|solveFieldStatically|" \
+             r"updateFieldsOnBoundaries|computeCurlB|computeCurlE|interpC2N)\s*\("
+    host = os.path.join(ROOT, "host")
+    for rel in ("include/ipic3d/app/simulator.h", "include/ipic3d/app/benchmark.h", "include/ipic3d/app/earth_deck.h",
+                "src/ipic3d.cc", "src/pic_tracer.cc"):
+        text = open(os.path.join(host, rel)).read()
+        code = "\n".join(line.split("//")[0] for line in text.splitlines())
+        assert not re.search(scalar, code), "%s calls a host scalar version" % rel
+    for dirpath, _, files in os.walk(os.path.join(host, "include")):
+        for f in files:
+            text = open(os.path.join(dirpath, f)).read()
+            code = "\n".join(line.split("//")[0] for line in text.splitlines())
+            assert not re.search(r"\b(moveParticles|exportParticles|importParticles)\s*\(", code), "%s defines a host mover/export/import" % f

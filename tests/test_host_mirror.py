@@ -110,6 +110,53 @@ def test_conserved_quantity_folds_bit_identical(mirror):
     assert bits_equal(got, want) and got[0] > 0 and got[2] > 0 and got[3] > 0
 
 
+@pytest.mark.parametrize("solver", ["forward", "leapfrog"])
+def test_host_scalar_field_and_projection_functions_bit_identical(mirror, solver):
+    """The host-callable scalar versions the mirror keeps for known-answer checks: projectToDensityField,
+    solveFieldForward / solveFieldLeapfrog, updateFieldsOnBoundaries, applied node by node in the order of the reference's
+    (commented) loop on the test.inp universe with seeded random fields, against the reference's own functions: every
+    bit of E, B, Bc and J equal.  (simulateSteps never calls them; its field phase is csrc/field_kernels.cu.)"""
+    path = os.path.join(GOLDEN_INPUTS, "test.inp")
+    props, cycles, npart = Props(), C.c_uint64(0), C.c_uint64(0)
+    h = C.c_void_p(mirror.ipic_mirror_create_from_inp(path.encode(), C.byref(props), C.byref(cycles), C.byref(npart)))
+    ref = Ref.from_inp(path)
+    rng = np.random.default_rng(5)
+    f = ref.field() * (1.0 + 0.25 * rng.standard_normal(ref.field().shape)) + 1e-9 * rng.standard_normal(ref.field().shape)
+    b = ref.bcfield() * (1.0 + 0.25 * rng.standard_normal(ref.bcfield().shape))
+    ref.field(f), ref.bcfield(b)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    mirror.ipic_mirror_set_fields(h, dp(f), dp(b), None)
+    n = int(props.size[0])
+    for x in range(n + 1):
+        for y in range(n + 1):
+            for z in range(n + 1):
+                ref.project_node(x, y, z)
+                assert mirror.ipic_mirror_node_op(h, 0, C.c_int64(x), C.c_int64(y), C.c_int64(z)) == 0
+    op = 1 if solver == "forward" else 2
+    for x in range(1, n + 2):
+        for y in range(1, n + 2):
+            for z in range(1, n + 2):
+                (ref.solve_forward_node if solver == "forward" else ref.solve_leapfrog_node)(x, y, z)
+                mirror.ipic_mirror_node_op(h, op, C.c_int64(x), C.c_int64(y), C.c_int64(z))
+    ref.update_boundaries()
+    mirror.ipic_mirror_node_op(h, 3, C.c_int64(0), C.c_int64(0), C.c_int64(0))
+    gf, gb, gj = np.zeros_like(f), np.zeros_like(b), np.zeros((props.grid_len(1), 3))
+    mirror.ipic_mirror_get_fields(h, dp(gf), dp(gb), dp(gj))
+    mirror.ipic_mirror_destroy(h)
+    assert np.abs(gj).max() > 0 and not bits_equal(gf, f)
+    assert bits_equal(gj, ref.density()) and bits_equal(gf, ref.field()) and bits_equal(gb, ref.bcfield())
+
+
+def test_host_scalar_trilinear_bit_identical(mirror):
+    rng = np.random.default_rng(11)
+    for _ in range(200):
+        corners, pos, vol = rng.standard_normal(24), rng.random(3), float(rng.random() + 0.5)
+        got = np.zeros(3)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        mirror.ipic_mirror_trilinear(dp(corners), dp(pos), C.c_double(vol), dp(got))
+        assert bits_equal(got, Ref.trilinear(corners, pos, vol))
+
+
 @pytest.mark.parametrize("deck", ["test.inp", "tiny.inp", "medium.inp"])
 def test_parser_matches_reference(mirror, deck):
     path = os.path.join(GOLDEN_INPUTS, deck)
