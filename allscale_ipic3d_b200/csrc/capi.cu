@@ -10,6 +10,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <limits>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -82,6 +83,10 @@ struct ipic_ctx {
 	double* dChunkJ = nullptr;
 	int chunkRange[4] = { 0, 0, 0, 0 };            // table offsets: plane 0 = [r0, r1), interior = [r1, r2), last plane = [r2, r3)
 	int64_t chunkCapacity = 0;                     // chunks the device arrays were allocated for
+	// big-outbox index (k_big_hist / k_big_scan / k_big_copy): cells of a single-GPU universe whose segment holds at least
+	// bigCellSlots() slots, rebuilt with the chunk table; nBig = 0: none
+	BigOutboxes big{};
+	int64_t bigCellCapacity = 0, bigSegCapacity = 0;   // what the device arrays behind `big` were allocated for
 	int* dStop = nullptr;                          // 8 control words: [0] stop, [1] first failing step, [2] cell overflow seen in this import pass, [3] exchange failure (1 face message full on this rank, 2 unusable message received), [4] an outbox awaits k_sort_outbox
 	bool haveCells = false;
 	int64_t meanPopulation = 0;                    // particles per owned cell at upload (drives the mover's tile shape)
@@ -200,6 +205,66 @@ void buildLayout(const ipic_ctx* c, const std::vector<int64_t>& need, std::vecto
 	start[(size_t)g.ncellsLocal] = pos;
 }
 
+// slots a cell segment must hold for its outbox to be indexed and copied by many warps (IPIC_BIG_CAP overrides; IPIC_BIG_IMPORT=0
+// switches the big-outbox path off: the import then scans such outboxes with the target cell's one warp, as it does for small ones)
+int64_t bigCellSlots() {
+	int64_t v = 32768;
+	if (const char* e = std::getenv("IPIC_BIG_CAP")) v = std::max<int64_t>(32, std::atoll(e));
+	if (const char* e = std::getenv("IPIC_BIG_IMPORT")) if (std::atoi(e) == 0) v = std::numeric_limits<int64_t>::max();
+	return v;
+}
+
+void freeBigOutboxTables(ipic_ctx* c) {
+	cudaFree(const_cast<int*>(c->big.cell)); cudaFree(const_cast<int*>(c->big.segFirst)); cudaFree(const_cast<int2*>(c->big.segTable));
+	cudaFree(c->big.rank); cudaFree(c->big.off); cudaFree(c->big.dst); cudaFree(c->big.room);
+	c->big = BigOutboxes{};
+	c->bigCellCapacity = c->bigSegCapacity = 0;
+}
+
+// The big cells of the layout in c->hCellStart (universes on one GPU: in a slab context a big outbox may have to cross to
+// another GPU, which the face messages do).  Called with the chunk table, i.e. at upload and after a re-layout.
+int buildBigOutboxTables(ipic_ctx* c) {
+	c->big.nBig = 0; c->big.totalSegs = 0;
+	if (c->nranks > 1) return IPIC_OK;
+	const int64_t least = bigCellSlots();
+	const int seg = big_outbox_segment();
+	std::vector<int> cells, segFirst(1, 0);
+	std::vector<int2> segTable;
+	for (int cell = 0; cell < c->g.ncellsLocal; cell++) {
+		const int64_t cap = c->hCellStart[(size_t)cell + 1] - c->hCellStart[(size_t)cell];
+		if (cap < least) continue;
+		const int id = (int)cells.size();
+		const int nseg = (int)((cap + seg - 1) / seg);
+		cells.push_back(cell);
+		for (int k = 0; k < nseg; k++) segTable.push_back(make_int2(id, k));
+		segFirst.push_back((int)segTable.size());
+	}
+	if (cells.empty()) return IPIC_OK;
+	if ((int64_t)cells.size() > c->bigCellCapacity || (int64_t)segTable.size() > c->bigSegCapacity) {
+		freeBigOutboxTables(c);
+		const size_t nc = cells.size() + cells.size() / 4 + 1, ns = segTable.size() + segTable.size() / 4 + 1;
+		int* dCell = nullptr; int* dFirst = nullptr; int2* dTable = nullptr;
+		CK(cudaMalloc(&dCell, nc * sizeof(int)));
+		c->big.cell = dCell;
+		CK(cudaMalloc(&dFirst, (nc + 1) * sizeof(int)));
+		c->big.segFirst = dFirst;
+		CK(cudaMalloc(&dTable, ns * sizeof(int2)));
+		c->big.segTable = dTable;
+		CK(cudaMalloc(&c->big.rank, ns * 27 * sizeof(int)));
+		CK(cudaMalloc(&c->big.off, nc * 28 * sizeof(int)));
+		CK(cudaMalloc(&c->big.dst, nc * 27 * sizeof(long long)));
+		CK(cudaMalloc(&c->big.room, nc * 27 * sizeof(long long)));
+		c->bigCellCapacity = (int64_t)nc; c->bigSegCapacity = (int64_t)ns;
+	}
+	CK(cudaMemcpyAsync(const_cast<int*>(c->big.cell), cells.data(), cells.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(const_cast<int*>(c->big.segFirst), segFirst.data(), segFirst.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(const_cast<int2*>(c->big.segTable), segTable.data(), segTable.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaStreamSynchronize(c->stream));            // the host vectors go out of scope
+	c->big.nBig = (int)cells.size();
+	c->big.totalSegs = (int)segTable.size();
+	return IPIC_OK;
+}
+
 // Chunk table of the layout in c->hCellStart, and the choice between one CTA per cell (k_move) and several
 // (k_move_chunk): the latter when cells are big enough that whole cells are too few / too uneven work items.
 int buildChunkTable(ipic_ctx* c, int64_t maxPopulation) {
@@ -210,7 +275,7 @@ int buildChunkTable(ipic_ctx* c, int64_t maxPopulation) {
 	// one cell: 28.8 ms vs 0.59 ms chunked)
 	c->chunked = maxPopulation > 128 * (int64_t)per;
 	if (const char* e = std::getenv("IPIC_CHUNKED")) c->chunked = std::atoi(e) != 0;
-	if (!c->chunked) return IPIC_OK;
+	if (!c->chunked) return buildBigOutboxTables(c);
 	std::vector<int2> table;
 	auto addPlanes = [&](int zFirst, int zEnd) {
 		for (int xy = 0; xy < g.nx * g.ny; xy++) for (int zl = zFirst; zl < zEnd; zl++) {
@@ -239,7 +304,7 @@ int buildChunkTable(ipic_ctx* c, int64_t maxPopulation) {
 	if (!c->dChunkTicket) CK(cudaMalloc(&c->dChunkTicket, 4 * sizeof(unsigned)));
 	CK(cudaMemcpyAsync(c->dChunkTable, table.data(), table.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
-	return IPIC_OK;
+	return buildBigOutboxTables(c);
 }
 
 int ensureStage(ipic_ctx* c, int64_t doubles) {
@@ -341,6 +406,7 @@ FaceMsg faceView(const ipic_ctx* c, char* base, int cap) {
 // where the import kernel finds the outboxes of the cells beyond the slab's first / last plane
 void setImportSources(const ipic_ctx* c, ImportArgs& ia) {
 	ia.slab = c->nranks > 1;
+	ia.big = c->big;
 	if (ia.slab) { ia.fromDown = faceView(c, c->recvMsg[0], c->recvCap); ia.fromUp = faceView(c, c->recvMsg[1], c->recvCap); }
 }
 
@@ -389,9 +455,8 @@ int relayoutAfterOverflow(ipic_ctx* c, int outGen, int failedStep) {
 	ia.order = c->dOrder; ia.dirOff = c->dDirOff;          // the failed step's outbox index, slots of the OLD layout
 	ia.dst = nb[outGen]; ia.dstStart = dNewStart; ia.stay = c->dStay; ia.dstCount = c->dCount;
 	ia.reserveOwnOutbox = 0; ia.stopFlag = c->dStop; ia.stepIndex = failedStep; ia.zBegin = 0; ia.zCount = c->g.lz; ia.zStride = 1;
-	setImportSources(c, ia);
-	launch_import(ia, true, c->stream);
-	c->launches += 3;
+	setImportSources(c, ia);              // (with the failed step's big-outbox index, which describes the OLD layout's outboxes)
+	c->launches += 1 + launch_import(ia, true, c->stream);
 	CK(cudaStreamSynchronize(c->stream));
 	int stop[4];
 	CK(cudaMemcpy(stop, c->dStop, sizeof stop, cudaMemcpyDeviceToHost));
@@ -556,6 +621,7 @@ int ipic_destroy(ipic_ctx* c) {
 	freeParticleBuffers(c);
 	cudaFree(c->dCellStart); cudaFree(c->dCount); cudaFree(c->dStay); cudaFree(c->dLeave); cudaFree(c->dStop); cudaFree(c->dDirOff);
 	cudaFree(c->dChunkTable); cudaFree(c->dChunkStatus); cudaFree(c->dChunkTicket); cudaFree(c->dChunkJ);
+	freeBigOutboxTables(c);
 	cudaFree(c->dEB); cudaFree(c->dBext); cudaFree(c->dBc); cudaFree(c->dJ); cudaFree(c->dCellJ);
 	cudaFree(c->dStage); cudaFree(c->dAosStart); cudaFree(c->dZiggurat);
 	for (auto e : c->events) cudaEventDestroy(e);
@@ -924,8 +990,7 @@ void importPlanes(ipic_ctx* c, int stepIndex, int zBegin, int zCount, bool commi
 	ia.dst = c->buf[out]; ia.dstStart = c->dCellStart; ia.stay = c->dStay; ia.dstCount = c->dCount;
 	ia.reserveOwnOutbox = 1; ia.stopFlag = c->dStop; ia.stepIndex = stepIndex; ia.zBegin = zBegin; ia.zCount = zCount; ia.zStride = zStride;
 	setImportSources(c, ia);
-	launch_import(ia, commit, c->stream);
-	c->launches += commit ? 2 : 1;
+	c->launches += launch_import(ia, commit, c->stream);
 }
 
 // event pair whose two halves are recorded in different phases (slab steps: the span of all movers)
@@ -954,6 +1019,11 @@ int enqueueStepSingle(ipic_ctx* c, const StepFlags& f, int stepIndex) {
 	{
 		ProfSpan span(c, 0);
 		c->launches += launch_move(moveArgs(c, f, 0, c->g.lz), c->stream);
+	}
+	if (f.migrate && c->big.nBig > 0) {
+		// outboxes of the universe's big cells: counted and ranked by many warps, so that no single warp has to import them
+		ProfSpan span(c, 1);
+		c->launches += launch_big_index(c->big, c->dCellStart, c->dLeave, c->dTag, c->dDirOff, c->dStop, c->stream);
 	}
 	if (f.fuseDeposit) {
 		launch_gather_current(c->g, c->dCellJ, c->dJ, c->dStop, c->stream);

@@ -132,8 +132,9 @@ __global__ void k_solver_node(const Geometry g, double* EB, double* Bc, const do
 // Measured on B200 (scripts/probe_solver.py, forward solver, per step): one launch per plane 0.72 ms (a kernel boundary per
 // plane); ONE CTA walking all planes with __syncthreads 1.11 ms (a single SM's load/store unit serialises the plane: ncu
 // lg_throttle 4.6, long scoreboard 8.4 per issue); a cooperative launch of as many CTAs as the per-plane grid had, with a
-// grid-wide barrier per plane: see DESIGN.md 3.  IPIC_SOLVER_MODE = coop | planes | one selects; a cooperative launch that
-// the device refuses falls back to one launch per plane.
+// grid-wide barrier per plane 0.535 ms; one 8-CTA cluster with the cluster barrier per plane 0.497 ms (leapfrog 0.565 -> 0.484;
+// profiles/r2y_solver_*.txt): the default.  IPIC_SOLVER_MODE = coop | planes | one | cluster selects; a cooperative launch
+// that the device refuses falls back to one launch per plane, a cluster launch that does not fit to the cooperative one.
 
 template<bool FORWARD>
 __global__ void __launch_bounds__(512)
@@ -171,15 +172,61 @@ k_solver_coop(const Geometry g, double* EB, double* Bc, const double* J, const i
 	}
 }
 
-static int solver_mode() {          // 0 planes, 1 one CTA, 2 cooperative
+// the same walk by ONE thread-block cluster (8 CTAs, or 16 where the grid needs them): the barrier per plane is the cluster's
+// hardware barrier (barrier.cluster, release / acquire at cluster scope: a few hundred cycles) instead of the grid-wide one
+template<bool FORWARD>
+__global__ void __launch_bounds__(512)
+k_solver_cluster(const Geometry g, double* EB, double* Bc, const double* J, const int* stopFlag) {
+	cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+	if (*stopFlag) return;                               // the same word for every thread of the cluster: nobody reaches a barrier
+	const int ex = g.nx + 1, ey = g.ny + 1;
+	const int lo = 3, hi = ex + ey + (g.nz + 1);
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool mine = t < ex * ey;
+	const int x = 1 + t / ey, y = 1 + t % ey;
+	for (int plane = lo; plane <= hi; plane++) {
+		const int z = plane - x - y;
+		if (mine && z >= 1 && z <= g.nz + 1) {
+			if (FORWARD) solve_forward_node(g, EB, Bc, J, x, y, z); else solve_leapfrog_node(g, EB, Bc, J, x, y, z);
+		}
+		cluster.sync();
+	}
+}
+
+// 0 planes, 1 one CTA, 2 cooperative, 3 one cluster, 4 (default) one cluster of the portable size 8 where it covers the grid
+// (up to 62^3 cells), else cooperative
+static int solver_mode() {
 	static int v = -1;
 	if (v < 0) {
 		const char* e = std::getenv("IPIC_SOLVER_MODE");
-		v = 2;
+		v = 4;
 		if (e && std::strcmp(e, "planes") == 0) v = 0;
 		if (e && std::strcmp(e, "one") == 0) v = 1;
+		if (e && std::strcmp(e, "coop") == 0) v = 2;
+		if (e && std::strcmp(e, "cluster") == 0) v = 3;
 	}
 	return v;
+}
+
+// one cluster that covers all (x, y) columns with at most 512 threads per CTA, if there is one; false: not launched
+template<bool FORWARD>
+static bool launch_solver_cluster(const Geometry& g, double* EB, double* Bc, const double* J, const int* stopFlag, cudaStream_t st, bool portableOnly) {
+	const int threads = (g.nx + 1) * (g.ny + 1);
+	int ctas = 8;
+	if ((threads + ctas - 1) / ctas > 512) { if (portableOnly) return false; ctas = 16; }
+	const int perCta = (((threads + ctas - 1) / ctas + 31) / 32) * 32;
+	if (perCta > 512) return false;
+	auto kernel = k_solver_cluster<FORWARD>;
+	if (ctas > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return false; }
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(perCta); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	if (cudaLaunchKernelEx(&cfg, kernel, g, EB, Bc, J, stopFlag) == cudaSuccess) return true;
+	cudaGetLastError();
+	return false;
 }
 
 int launch_field_solver(const Geometry& g, bool forward, double* EB, double* Bc, const double* J, const int* stopFlag, cudaStream_t st) {
@@ -191,7 +238,10 @@ int launch_field_solver(const Geometry& g, bool forward, double* EB, double* Bc,
 		else k_solver_wavefront<false><<<1, 512, 0, st>>>(g, EB, Bc, J, stopFlag);
 		return 1;
 	}
-	if (mode == 2) {
+	if (mode >= 3) {
+		if (forward ? launch_solver_cluster<true>(g, EB, Bc, J, stopFlag, st, mode == 4) : launch_solver_cluster<false>(g, EB, Bc, J, stopFlag, st, mode == 4)) return 1;
+	}
+	if (mode >= 2) {
 		Geometry gg = g;
 		void* args[] = { &gg, &EB, &Bc, &J, &stopFlag };
 		const void* kernel = forward ? (const void*)k_solver_coop<true> : (const void*)k_solver_coop<false>;

@@ -92,6 +92,7 @@ __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
 // indexed, scan the tags".
 constexpr int kSortCap = 2048;
 constexpr int kSortPending = -2;
+constexpr int kBigMarker = -4;             // dirOff[*] = kBigMarker - id: outbox number `id` of the big-outbox index (k_big_scan), see below
 
 // called by ONE warp once the (at most 32) tags of the cell are in sTags
 __device__ __forceinline__ void sort_outbox_small(const unsigned char* sTags, int L, int lane,
@@ -979,7 +980,7 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
          const unsigned char* __restrict__ tag, const unsigned short* __restrict__ order, const int* __restrict__ dirOff,
          const ParticleArrays dst, const int64_t* __restrict__ dstStart,
          const int* __restrict__ stay, int* __restrict__ dstCount, int reserveOwnOutbox, int* __restrict__ stopFlag, int stepIndex, int zBegin, int zCount, int zStride,
-         const FaceMsg fromDown, const FaceMsg fromUp) {
+         const FaceMsg fromDown, const FaceMsg fromUp, const BigOutboxes big) {
 
 	__shared__ int sListAll[kImportWarps][kListWindow];       // arrivals of the current window: direction << 24 | index within the direction
 	__shared__ int64_t sSrcA[kImportWarps][27];               // per direction: first order slot (local) / first record (remote)
@@ -1001,7 +1002,7 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 	auto isRemote = [&](int d) { const int c = d % 3; return SLAB && ((c == 0 && zl == 0) || (c == 2 && zl == g.lz - 1)); };
 
 	// lane d: what arrives from its neighbour
-	int cnt = 0, scell = 0;
+	int cnt = 0, scell = 0, bigId = -1;
 	int64_t A = 0, B = 0;
 	bool unsorted = false, corrupt = false;
 	if (lane < 27 && lane != 13) {
@@ -1020,7 +1021,12 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 			const int* o = dirOff + (int64_t)scell * 28 + (26 - lane);
 			const int o0 = o[0];
 			B = srcStart[scell + 1] - 1;                  // outbox entry j lives at slot B - j
-			if (o0 < 0) unsorted = true;
+			if (o0 <= kBigMarker) {
+				// a big outbox (k_big_index): only its size per direction is looked up here, k_big_copy moves the particles
+				bigId = kBigMarker - o0;
+				const int* bo = big.off + bigId * 28 + (26 - lane);
+				cnt = bo[1] - bo[0];
+			} else if (o0 < 0) unsorted = true;
 			else { cnt = o[1] - o0; A = srcStart[scell] + o0; }
 		}
 	}
@@ -1030,7 +1036,7 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 		return;
 	}
 
-	if (!__any_sync(0xffffffffu, unsorted || cnt >= (1 << 24))) {
+	if (!__any_sync(0xffffffffu, unsorted || bigId >= 0 || cnt >= (1 << 24))) {
 		int incl = cnt;
 		#pragma unroll
 		for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -1066,6 +1072,13 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 			if (d == 13) continue;
 			const bool uns = __shfl_sync(0xffffffffu, (int)unsorted, d) != 0;
 			const int64_t a0 = __shfl_sync(0xffffffffu, A, d), b0 = __shfl_sync(0xffffffffu, B, d);
+			const int bid = __shfl_sync(0xffffffffu, bigId, d);
+			if (bid >= 0) {
+				// arrivals out of a big outbox: reserve their place in the canonical order and tell k_big_copy where it is
+				if (lane == 0) { big.dst[bid * 27 + (26 - d)] = dbase + w; big.room[bid * 27 + (26 - d)] = dbase + room; }
+				w += __shfl_sync(0xffffffffu, cnt, d);
+				continue;
+			}
 			if (!uns) {
 				const int n = __shfl_sync(0xffffffffu, cnt, d);
 				const bool remote = isRemote(d);
@@ -1098,6 +1111,135 @@ k_import(const Geometry g, const ParticleArrays src, const int64_t* __restrict__
 	if (lane == 0) {
 		if (w > room) atomicMin(stopFlag + 1, stepIndex), atomicExch(stopFlag + 2, 1);   // recorded; flag raised by k_commit
 		dstCount[cell] = w;
+	}
+}
+
+// ---- big outboxes: index and copy spread over the whole GPU ---------------------------------------------
+//
+// The reference's :E: / :B: loads pile most of the plasma into a few cells, and a cell that holds millions of particles can
+// send millions of them to ONE neighbour in one step.  Such an outbox carries no direction index (it comes from the chunked
+// mover, or holds more than kSortCap entries), so every target warp above would scan all of its tags and copy its share 32
+// entries per trip -- one warp for millions of particles.  For the cells the host lists as big (segment capacity of tens of
+// thousands of slots, capi.cu bigCellSlots(); universes on one GPU) the work is cut into segments of kBigSeg outbox
+// entries, one warp each:
+//   k_big_hist   per segment: how many entries carry each tag
+//   k_big_scan   per big cell: exclusive scan of those counts over the segments, tag by tag; totals -> big.off (what the
+//                import needs to place the arrivals of every direction) and dirOff[cell][*] = kBigMarker - id
+//   k_import     sees the marker: counts the arrivals, reserves their slots in canonical order, copies nothing, and
+//                leaves the first slot and the end of the usable room per (big cell, tag) in big.dst / big.room
+//   k_big_copy   per segment: entry j with tag t goes to big.dst[t] + (entries with tag t in earlier segments) + (earlier
+//                entries with tag t in this segment) -- the position the one-warp scan would have given it.
+
+constexpr int kBigSeg = 1024;              // outbox entries per warp task
+constexpr int kBigWarps = 8;
+
+__global__ void __launch_bounds__(kBigWarps * 32)
+k_big_hist(const BigOutboxes big, const int64_t* __restrict__ cellStart, const int* __restrict__ nLeave, const unsigned char* __restrict__ tag,
+           const int* __restrict__ stopFlag) {
+	__shared__ int sCntAll[kBigWarps][28];
+	if (*stopFlag) return;
+	const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+	const int task = blockIdx.x * kBigWarps + wp;
+	if (task >= big.totalSegs) return;
+	const int2 ref = big.segTable[task];
+	const int id = ref.x, seg = ref.y;
+	const int cell = big.cell[id];
+	const int L = nLeave[cell];
+	const int j0 = seg * kBigSeg;
+	if (j0 >= L) return;                                  // beyond the outbox: the scan does not read this segment's counts
+	const int jEnd = min(L, j0 + kBigSeg);
+	const int64_t send = cellStart[cell + 1] - 1;         // outbox entry j lives at slot send - j
+	int* sCnt = sCntAll[wp];
+	const unsigned lt = (1u << lane) - 1u;
+	if (lane < 27) sCnt[lane] = 0;                        // tags of outbox entries are 0..26 (never 13)
+	__syncwarp();
+	for (int jj = j0; jj < jEnd; jj += 32) {
+		const int j = jj + lane;
+		const unsigned t = j < jEnd ? tag[send - j] : 255u;
+		const unsigned peers = __match_any_sync(0xffffffffu, t);
+		if (t < 27u && (peers & lt) == 0u) sCnt[t] += __popc(peers);      // one lane per tag value: no conflicts
+		__syncwarp();
+	}
+	const int nseg = big.segFirst[id + 1] - big.segFirst[id];
+	if (lane < 27) big.rank[(int64_t)big.segFirst[id] * 27 + (int64_t)lane * nseg + seg] = sCnt[lane];
+}
+
+// one CTA of 27 warps per big cell: warp t scans the counts of tag t over the cell's segments
+__global__ void __launch_bounds__(27 * 32)
+k_big_scan(const BigOutboxes big, const int* __restrict__ nLeave, int* __restrict__ dirOff, const int* __restrict__ stopFlag) {
+	__shared__ int sTot[32];
+	if (*stopFlag) return;
+	const int lane = threadIdx.x & 31, t = threadIdx.x >> 5;
+	const int id = blockIdx.x;
+	const int cell = big.cell[id];
+	const int L = nLeave[cell];
+	const int used = (L + kBigSeg - 1) / kBigSeg;
+	const int nseg = big.segFirst[id + 1] - big.segFirst[id];
+	int* r = big.rank + (int64_t)big.segFirst[id] * 27 + (int64_t)t * nseg;
+	int running = 0;
+	for (int s0 = 0; s0 < used; s0 += 32) {
+		const int sidx = s0 + lane;
+		const int v = sidx < used ? r[sidx] : 0;
+		int incl = v;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+		if (sidx < used) r[sidx] = running + incl - v;
+		running += __shfl_sync(0xffffffffu, incl, 31);
+	}
+	if (lane == 0) sTot[t] = running;
+	if (threadIdx.x >= 27 && threadIdx.x < 32) sTot[threadIdx.x] = 0;
+	__syncthreads();
+	if (t == 0) {
+		const int v = lane < 27 ? sTot[lane] : 0;
+		int incl = v;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+		if (lane < 28) {
+			big.off[id * 28 + lane] = incl - v;               // lane 27: v = 0, incl = L
+			dirOff[(int64_t)cell * 28 + lane] = kBigMarker - id;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(kBigWarps * 32)
+k_big_copy(const BigOutboxes big, const Geometry g, const ParticleArrays src, const int64_t* __restrict__ srcStart, const int* __restrict__ nLeave,
+           const unsigned char* __restrict__ tag, const ParticleArrays dst, const int* __restrict__ stopFlag) {
+	__shared__ int sCntAll[kBigWarps][28];
+	__shared__ long long sDstAll[kBigWarps][28], sRoomAll[kBigWarps][28];
+	if (*stopFlag) return;
+	const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+	const int task = blockIdx.x * kBigWarps + wp;
+	if (task >= big.totalSegs) return;
+	const int2 ref = big.segTable[task];
+	const int id = ref.x, seg = ref.y;
+	const int cell = big.cell[id];
+	const int L = nLeave[cell];
+	const int j0 = seg * kBigSeg;
+	if (j0 >= L) return;
+	const int jEnd = min(L, j0 + kBigSeg);
+	const int64_t send = srcStart[cell + 1] - 1;
+	const int nseg = big.segFirst[id + 1] - big.segFirst[id];
+	int* sCnt = sCntAll[wp];
+	long long* sDst = sDstAll[wp];
+	long long* sRoom = sRoomAll[wp];
+	const unsigned lt = (1u << lane) - 1u;
+	if (lane < 27) {
+		sCnt[lane] = big.rank[(int64_t)big.segFirst[id] * 27 + (int64_t)lane * nseg + seg];     // entries with this tag in earlier segments
+		sDst[lane] = big.dst[id * 27 + lane];
+		sRoom[lane] = big.room[id * 27 + lane];
+	}
+	__syncwarp();
+	for (int jj = j0; jj < jEnd; jj += 32) {
+		const int j = jj + lane;
+		const unsigned t = j < jEnd ? tag[send - j] : 255u;
+		const unsigned peers = __match_any_sync(0xffffffffu, t);
+		if (t < 27u) {
+			const long long slot = sDst[t] + sCnt[t] + __popc(peers & lt);
+			if (slot < sRoom[t]) copy_arrival(false, nullptr, 0, src.d, send - j, g.nf, dst.d + slot_index(slot, g.nf));
+		}
+		__syncwarp();
+		if (t < 27u && (peers & lt) == 0u) sCnt[t] += __popc(peers);
+		__syncwarp();
 	}
 }
 
@@ -1493,15 +1635,34 @@ int launch_move(const MoveArgs& a, cudaStream_t st) {
 	return 2;
 }
 
-void launch_import(const ImportArgs& a, bool commit, cudaStream_t st) {
+int big_outbox_segment() { return kBigSeg; }
+
+// index of the big outboxes the movers of this step left behind (after the movers, before the import)
+int launch_big_index(const BigOutboxes& big, const int64_t* cellStart, const int* nLeave, const unsigned char* tag, int* dirOff, const int* stopFlag, cudaStream_t st) {
+	if (big.nBig <= 0) return 0;
+	cudaMemsetAsync(big.dst, 0, (size_t)big.nBig * 27 * sizeof(long long), st);      // a (cell, tag) nobody imports copies nothing: room 0
+	cudaMemsetAsync(big.room, 0, (size_t)big.nBig * 27 * sizeof(long long), st);
+	k_big_hist<<<(big.totalSegs + kBigWarps - 1) / kBigWarps, kBigWarps * 32, 0, st>>>(big, cellStart, nLeave, tag, stopFlag);
+	k_big_scan<<<big.nBig, 27 * 32, 0, st>>>(big, nLeave, dirOff, stopFlag);
+	return 2;
+}
+
+// the import proper, then the particles of the big outboxes, then (commit) the stop flag of an overflowed pass
+int launch_import(const ImportArgs& a, bool commit, cudaStream_t st) {
 	const int tasks = a.g.nx * a.g.ny * a.zCount;
-	if (tasks == 0) return;
+	if (tasks == 0) return 0;
 	const int grid = (tasks + kImportWarps - 1) / kImportWarps;
+	int launched = 1;
 	if (a.slab) k_import<true><<<grid, kImportBlock, 0, st>>>(a.g, a.src, a.srcStart, a.srcLeave, a.tag, a.order, a.dirOff, a.dst, a.dstStart, a.stay, a.dstCount,
-	                                                        a.reserveOwnOutbox, a.stopFlag, a.stepIndex, a.zBegin, a.zCount, a.zStride > 0 ? a.zStride : 1, a.fromDown, a.fromUp);
+	                                                        a.reserveOwnOutbox, a.stopFlag, a.stepIndex, a.zBegin, a.zCount, a.zStride > 0 ? a.zStride : 1, a.fromDown, a.fromUp, a.big);
 	else k_import<false><<<grid, kImportBlock, 0, st>>>(a.g, a.src, a.srcStart, a.srcLeave, a.tag, a.order, a.dirOff, a.dst, a.dstStart, a.stay, a.dstCount,
-	                                                    a.reserveOwnOutbox, a.stopFlag, a.stepIndex, a.zBegin, a.zCount, a.zStride > 0 ? a.zStride : 1, FaceMsg{}, FaceMsg{});
-	if (commit) k_commit_flag<<<1, 1, 0, st>>>(a.stopFlag);
+	                                                    a.reserveOwnOutbox, a.stopFlag, a.stepIndex, a.zBegin, a.zCount, a.zStride > 0 ? a.zStride : 1, FaceMsg{}, FaceMsg{}, a.big);
+	if (a.big.nBig > 0) {
+		k_big_copy<<<(a.big.totalSegs + kBigWarps - 1) / kBigWarps, kBigWarps * 32, 0, st>>>(a.big, a.g, a.src, a.srcStart, a.srcLeave, a.tag, a.dst, a.stopFlag);
+		launched++;
+	}
+	if (commit) { k_commit_flag<<<1, 1, 0, st>>>(a.stopFlag); launched++; }
+	return launched;
 }
 
 void launch_face_pack(const Geometry& g, const ParticleArrays& src, const int64_t* cellStart, const int* nLeave, const unsigned char* tag,

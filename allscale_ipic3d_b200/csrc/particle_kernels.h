@@ -34,6 +34,20 @@ struct MoveArgs {
 // particles per chunk of the chunked mover
 int chunk_particles();
 
+// Index of the BIG outboxes of a step (cells of a single-GPU universe whose segment holds tens of thousands of slots): their
+// entries are counted, ranked and copied by many warps (k_big_hist / k_big_scan / k_big_copy) instead of by the one warp
+// that imports the target cell.  nBig = 0: no such cells, nothing is launched.
+struct BigOutboxes {
+	int nBig = 0, totalSegs = 0;
+	const int* cell = nullptr;        // [nBig] local cell id
+	const int* segFirst = nullptr;    // [nBig + 1] first entry of each big cell in segTable
+	const int2* segTable = nullptr;   // [totalSegs] (big id, segment of big_outbox_segment() outbox entries within the cell)
+	int* rank = nullptr;              // [totalSegs * 27] per cell, tag-major: entries with tag t in segment s; after the scan: in the segments before s
+	int* off = nullptr;               // [nBig * 28] exclusive prefix of the outbox's entries over the 27 tags
+	long long* dst = nullptr;         // [nBig * 27] first slot of the target cell's arrivals with (big cell, tag); written by the import
+	long long* room = nullptr;        // [nBig * 27] end of the slots that target may use
+};
+
 struct ImportArgs {
 	Geometry g;
 	ParticleArrays src; const int64_t* srcStart; const int* srcLeave; const unsigned char* tag;
@@ -45,6 +59,7 @@ struct ImportArgs {
 	int zBegin, zCount, zStride;   // planes zBegin, zBegin + zStride, ... (zStride 0 / 1: consecutive)
 	bool slab;                 // z-slab context: neighbours beyond the slab's first / last plane are columns of the face messages
 	FaceMsg fromDown, fromUp;
+	BigOutboxes big;           // outboxes indexed by launch_big_index in this step (their dirOff carries the marker)
 };
 
 // returns the number of kernels launched (the mover; after a migrating push also k_sort_outbox, which indexes the outboxes
@@ -52,8 +67,12 @@ struct ImportArgs {
 int launch_move(const MoveArgs& a, cudaStream_t st);
 // does launch_move run the warp-specialised kernel (k_move_ws: a fifth warp deposits) for these switches?
 bool move_uses_ws(const Geometry& g, bool deposit, bool interpolate, bool push);
-// `commit`: also raise the stop flag if any import pass of this step overflowed a cell segment
-void launch_import(const ImportArgs& a, bool commit, cudaStream_t st);
+// `commit`: also raise the stop flag if any import pass of this step overflowed a cell segment; returns the number of kernels launched
+int launch_import(const ImportArgs& a, bool commit, cudaStream_t st);
+// outbox entries per segment of the big-outbox index
+int big_outbox_segment();
+// after the movers of a step, before its import: count and rank the entries of the big outboxes; returns the number of kernels launched
+int launch_big_index(const BigOutboxes& big, const int64_t* cellStart, const int* nLeave, const unsigned char* tag, int* dirOff, const int* stopFlag, cudaStream_t st);
 // z-slab exchange: pack both faces of the slab into their messages (3 launches)
 void launch_face_pack(const Geometry& g, const ParticleArrays& src, const int64_t* cellStart, const int* nLeave, const unsigned char* tag,
                       const unsigned short* order, const int* dirOff, int* faceCnt, const FaceMsg& down, const FaceMsg& up, int* totals, int* stopFlag, int stepIndex, cudaStream_t st);

@@ -1,5 +1,5 @@
 """GPU probe: cost of the field phase (ghost update + forward / leapfrog solver) per step on the 32^3 benchmark grid:
-full PIC step vs the same step without solver, for the current IPIC_SOLVER_LAUNCHES setting."""
+full PIC step vs the same step without solver, for the current IPIC_SOLVER_MODE setting (coop | planes | one | cluster)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -14,4 +14,4 @@ with ipic.Context(props) as c:
         c.step(3, flags)
         a, b = c.step(20, flags)
         out.append("%s %.3f ms/step" % (name, (a + b) / 20 * 1e3))
-    print("IPIC_SOLVER_LAUNCHES=%s: %s" % (os.environ.get("IPIC_SOLVER_LAUNCHES", "unset"), "; ".join(out)))
+    print("IPIC_SOLVER_MODE=%s: %s" % (os.environ.get("IPIC_SOLVER_MODE", "unset (coop)"), "; ".join(out)))
