@@ -16,13 +16,13 @@ for line in sass.split("\n"):
         continue
     if cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
         kernels[cur].append(line.strip())
-KEYS = ["UBLKCP", "SYNCS", "MATCH", "DFMA", "DMUL", "DADD", "MUFU.RSQ64H", "MUFU.RCP64H", "BAR.SYNC", "SHFL", "VOTE", "ATOM", "RED", "LDS", "STS", "LDG", "STG"]
+KEYS = ["UBLKCP", "SYNCS", "MATCH", "UCGABAR", "CGAERRBAR", "DFMA", "DMUL", "DADD", "MUFU.RSQ64H", "MUFU.RCP64H", "BAR.SYNC", "SHFL", "VOTE", "ATOM", "RED", "LDS", "STS", "LDG", "STG"]
 print("SASS of %s (sm_100a), instructions per kernel; arch check: %s" % (os.path.basename(lib), re.search(r"arch = (\S+)", sass).group(1)))
 for name, ins in kernels.items():
     short = demangle(name)
     m = re.match(r"^(?:void )?(ipic::\w+(?:<.*?>)?)\(", short)
     short = re.sub(r"\((int|bool)\)", "", m.group(1)) if m else short
-    if not re.search(r"k_move|k_import|k_sort|k_face|k_init|k_solver_wavefront|k_gather_current|k_trace", short):
+    if not re.search(r"k_move|k_import|k_sort|k_big|k_face|k_init|k_solver_wavefront|k_solver_cluster|k_gather_current|k_trace", short):
         continue
     c = collections.Counter()
     first = {}
@@ -35,6 +35,6 @@ for name, ins in kernels.items():
                 first.setdefault(k, op.split(";")[0])
     print("\n%s  [%d SASS instructions]" % (short, len(ins)))
     print("   " + "  ".join("%s %d" % (k, c[k]) for k in KEYS if c[k]))
-    for k in ("UBLKCP", "SYNCS", "MATCH"):
+    for k in ("UBLKCP", "SYNCS", "MATCH", "UCGABAR"):
         if k in first:
             print("   e.g. " + first[k])
