@@ -99,6 +99,14 @@ namespace ipic3d {
 		return EXIT_SUCCESS;
 	}
 
+	// any particle generator on the benchmark grid (reference hdr/benchmark.h:57-79): what the four loads below are special cases of
+	template<typename Distribution>
+	int processDistribution(const Distribution& dist, std::uint64_t numParticles, std::uint64_t numTimeSteps) {
+		std::cout << "Creating Particles ..." << std::endl;
+		Universe universe = createUniverseFromDistribution(detail::benchmarkProperties(), detail::benchmarkInit(), numParticles, dist);
+		return processUniverse(universe, numParticles, numTimeSteps);
+	}
+
 	inline int processLoad(char kind, std::uint64_t numParticles, std::uint64_t numTimeSteps) {
 		std::cout << "Creating Particles ..." << std::endl;
 		Universe universe = benchmarkUniverse(kind, numParticles, numTimeSteps);

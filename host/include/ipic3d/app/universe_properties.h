@@ -11,7 +11,9 @@
 
 namespace ipic3d {
 
-	inline std::ostream& operator<<(std::ostream& out, const UseCase& useCase) { return out << (useCase == UseCase::Dipole ? "Dipole" : "Test"); }
+	// "Dipole" / "Test"; anything else reads as "Test", like the parser's fallback (reference hdr/universe_properties.h:15-30)
+	inline std::string getUseCaseName(const UseCase& useCase) { return useCase == UseCase::Dipole ? "Dipole" : "Test"; }
+	inline std::ostream& operator<<(std::ostream& out, const UseCase& useCase) { return out << getUseCaseName(useCase); }
 
 	struct UniverseProperties {
 		UseCase useCase = UseCase::Dipole;

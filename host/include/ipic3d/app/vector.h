@@ -8,6 +8,7 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <cstdlib>
@@ -65,6 +66,7 @@ namespace ipic3d {
 	Vector3<T> operator/(Vector3<T> a, S f) { return a /= f; }
 
 	template<typename T> T sumOfSquares(const Vector3<T>& v) { T s = T(); s += v.x * v.x; s += v.y * v.y; s += v.z * v.z; return s; }
+	template<typename T> T norm(const Vector3<T>& v) { return std::sqrt(sumOfSquares(v)); }        // reference hdr/vector.h:12-15
 	template<typename T> Vector3<T> crossProduct(const Vector3<T>& a, const Vector3<T>& b) {
 		return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x };
 	}
@@ -80,6 +82,7 @@ namespace ipic3d {
 	namespace utils {
 		template<std::size_t D> using Coordinate = coordinate_type;     // only D == 3 exists on this path
 		template<std::size_t D> using Size = coordinate_type;
+		template<typename T, std::size_t D> using vec = Vector3<T>;
 	}
 
 	// dense, value-initialised 3-D container (the reference's allscale Grid<T,3>); z runs fastest
