@@ -50,3 +50,23 @@ def test_binding_drives_the_reference_data_model(tmp_path):
     text = (a / "test.out").read_text()
     assert text == (b / "test.out").read_text()
     assert "Total: 257060" in text                      # the reference's result for this deck at this commit
+
+
+def test_binding_under_the_benchmark_driver(tmp_path):
+    """`ipic3d :U:N` (processUniverse: two simulateSteps calls on one universe, hdr/benchmark.h:38,43) through the binding and
+    the test double: the particle positions the reference dumps before and after (DUMP_PARTICLE_POSITION) are identical."""
+    mock_dir = tmp_path / "mock"
+    mock_dir.mkdir()
+    subprocess.check_call(["gcc", "-O2", "-std=gnu11", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"),
+                           os.path.join(ROOT, "tests", "mock_abi", "mock_ipic3d_b200.c"), "-L" + os.path.join(ROOT, "oracle"), "-lipic3d_oracle",
+                           "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", str(mock_dir / "libipic3d_b200.so")])
+    a, b = tmp_path / "bound", tmp_path / "ref"
+    a.mkdir(); b.mkdir()
+    env = dict(os.environ, DUMP_PARTICLE_POSITION="1")
+    got = run(BOUND, a, dict(env, LD_LIBRARY_PATH=str(mock_dir) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", "")), args=(":U:60000",))
+    assert got.returncode == 0 and "Throughput:" in got.stdout, got.stderr[-1000:]
+    want = run(os.path.join(REF, "ipic3d_ref"), b, env, args=(":U:60000",))
+    assert want.returncode == 0
+    for name in ("t_begin.txt", "t_end.txt"):
+        assert (a / name).read_text() == (b / name).read_text(), name
+    assert (a / "t_begin.txt").read_text() != (a / "t_end.txt").read_text()
