@@ -52,6 +52,27 @@ def test_binding_drives_the_reference_data_model(tmp_path):
     assert "Total: 257060" in text                      # the reference's result for this deck at this commit
 
 
+def build_mock(tmp_path):
+    mock_dir = tmp_path / "mock"
+    mock_dir.mkdir()
+    subprocess.check_call(["gcc", "-O2", "-std=gnu11", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"),
+                           os.path.join(ROOT, "tests", "mock_abi", "mock_ipic3d_b200.c"), "-L" + os.path.join(ROOT, "oracle"), "-lipic3d_oracle",
+                           "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", str(mock_dir / "libipic3d_b200.so")])
+    return dict(os.environ, LD_LIBRARY_PATH=str(mock_dir) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+
+
+def test_reference_simulation_tests_through_the_binding(tmp_path):
+    """The reference's simulation_test.cc with the reference's own headers and the binding (oracle/_ref/ut_binding): its
+    seven cases (Boris straight line, Larmor 1000 steps, ExB drift 5000 steps, migration / reflection on 3^3 and 4^3 grids, all
+    through simulateSteps / simulateStep on universes edited between the calls) pass against the test double of the C ABI."""
+    exe = os.path.join(REF, "ut_binding", "simulation_test")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ut_binding not built")
+    out = subprocess.run([exe], cwd=ROOT, env=build_mock(tmp_path), capture_output=True, text=True, timeout=900)
+    text = out.stdout + out.stderr
+    assert out.returncode == 0 and "7 cases, 0 failed" in text, text[-2000:]
+
+
 def test_binding_under_the_benchmark_driver(tmp_path):
     """`ipic3d :U:N` (processUniverse: two simulateSteps calls on one universe, hdr/benchmark.h:38,43) through the binding and
     the test double: the particle positions the reference dumps before and after (DUMP_PARTICLE_POSITION) are identical."""
