@@ -22,6 +22,15 @@ def run(exe, cwd, env=None, args=(DECK,)):
     return subprocess.run([exe, *args], cwd=cwd, env=env, capture_output=True, text=True, timeout=900)
 
 
+def build_mock(tmp_path):
+    mock_dir = tmp_path / "mock"
+    mock_dir.mkdir()
+    subprocess.check_call(["gcc", "-O2", "-std=gnu11", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"),
+                           os.path.join(ROOT, "tests", "mock_abi", "mock_ipic3d_b200.c"), "-L" + os.path.join(ROOT, "oracle"), "-lipic3d_oracle",
+                           "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", str(mock_dir / "libipic3d_b200.so")])
+    return dict(os.environ, LD_LIBRARY_PATH=str(mock_dir) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+
+
 def test_binding_links_the_product_library_and_has_no_cpu_path(tmp_path):
     needed = subprocess.run(["readelf", "-d", BOUND], capture_output=True, text=True).stdout
     assert "libipic3d_b200.so" in needed and "oracle" not in needed
@@ -35,14 +44,9 @@ def test_binding_links_the_product_library_and_has_no_cpu_path(tmp_path):
 
 def test_binding_drives_the_reference_data_model(tmp_path):
     """Reference main + binding + test double of the C ABI (CPU oracle): same test.out as the reference itself."""
-    mock_dir = tmp_path / "mock"
-    mock_dir.mkdir()
-    subprocess.check_call(["gcc", "-O2", "-std=gnu11", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"),
-                           os.path.join(ROOT, "tests", "mock_abi", "mock_ipic3d_b200.c"), "-L" + os.path.join(ROOT, "oracle"), "-lipic3d_oracle",
-                           "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", str(mock_dir / "libipic3d_b200.so")])
     a, b = tmp_path / "bound", tmp_path / "ref"
     a.mkdir(); b.mkdir()
-    env = dict(os.environ, LD_LIBRARY_PATH=str(mock_dir) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    env = build_mock(tmp_path)
     got = run(BOUND, a, env)
     assert got.returncode == 0, got.stderr[-1000:]
     want = run(os.path.join(REF, "ipic3d_ref"), b)
@@ -50,15 +54,6 @@ def test_binding_drives_the_reference_data_model(tmp_path):
     text = (a / "test.out").read_text()
     assert text == (b / "test.out").read_text()
     assert "Total: 257060" in text                      # the reference's result for this deck at this commit
-
-
-def build_mock(tmp_path):
-    mock_dir = tmp_path / "mock"
-    mock_dir.mkdir()
-    subprocess.check_call(["gcc", "-O2", "-std=gnu11", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"),
-                           os.path.join(ROOT, "tests", "mock_abi", "mock_ipic3d_b200.c"), "-L" + os.path.join(ROOT, "oracle"), "-lipic3d_oracle",
-                           "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", str(mock_dir / "libipic3d_b200.so")])
-    return dict(os.environ, LD_LIBRARY_PATH=str(mock_dir) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
 
 
 def test_reference_simulation_tests_through_the_binding(tmp_path):
@@ -76,15 +71,10 @@ def test_reference_simulation_tests_through_the_binding(tmp_path):
 def test_binding_under_the_benchmark_driver(tmp_path):
     """`ipic3d :U:N` (processUniverse: two simulateSteps calls on one universe, hdr/benchmark.h:38,43) through the binding and
     the test double: the particle positions the reference dumps before and after (DUMP_PARTICLE_POSITION) are identical."""
-    mock_dir = tmp_path / "mock"
-    mock_dir.mkdir()
-    subprocess.check_call(["gcc", "-O2", "-std=gnu11", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"),
-                           os.path.join(ROOT, "tests", "mock_abi", "mock_ipic3d_b200.c"), "-L" + os.path.join(ROOT, "oracle"), "-lipic3d_oracle",
-                           "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", str(mock_dir / "libipic3d_b200.so")])
     a, b = tmp_path / "bound", tmp_path / "ref"
     a.mkdir(); b.mkdir()
     env = dict(os.environ, DUMP_PARTICLE_POSITION="1")
-    got = run(BOUND, a, dict(env, LD_LIBRARY_PATH=str(mock_dir) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", "")), args=(":U:60000",))
+    got = run(BOUND, a, dict(build_mock(tmp_path), DUMP_PARTICLE_POSITION="1"), args=(":U:60000",))
     assert got.returncode == 0 and "Throughput:" in got.stdout, got.stderr[-1000:]
     want = run(os.path.join(REF, "ipic3d_ref"), b, env, args=(":U:60000",))
     assert want.returncode == 0
