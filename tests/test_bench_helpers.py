@@ -5,6 +5,9 @@ import os
 import types
 
 import numpy as np
+import pytest
+
+import harness
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
@@ -42,3 +45,24 @@ def test_both_arms_describe_the_same_workload():
             assert set(cfg) == {"workload", "particles", "particles_per_gpu", "grid", "dt"}
             assert cfg["particles_per_gpu"] * world <= cfg["particles"] < (cfg["particles_per_gpu"] + 1) * world
     assert bench.workload_config(types.SimpleNamespace(workload="uniform", grid=32, particles_per_gpu=32_000_000), 8)["particles"] == 256_000_000
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's own CPU loop on the box's host threads) on a small universe: one JSON line
+    with the contract's keys, the b200 arm's `config`, an e2e that repeats the value with zero bytes copied, and a cpu_baseline
+    describing this very run."""
+    import json, subprocess, sys
+    if not harness.Ref.available(True):
+        pytest.skip("oracle/_ref not built")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--particles-per-gpu", "200000", "--steps", "3", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-1000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 3 and line["warmup"] == 1
+    assert line["unit"] == "particle-pushes/s" and line["dtype"] == "f64" and line["vs_baseline"] is None and line["value"] > 0
+    assert line["config"] == bench.workload_config(types.SimpleNamespace(workload="uniform", grid=32, particles_per_gpu=200000), 1)
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["value"] == line["value"] and line["cpu_baseline"]["cores"] >= 1
+    assert line["with_deposit"]["value"] > 0
